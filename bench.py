@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Dr.Jit data-parallel primitive path on B200.
+
+One "step" = one pass of the primitive suite over synthetic fmix32 inputs resident in HBM
+(generator: ext/drjit-core/tests/reductions.cpp:5-13; sizes: BASELINE.json configs):
+
+    sum f32 2^28 | block_reduce(Add,256) f32 2^28 | dot f32 2^28 | exclusive prefix_sum u32 2^30 |
+    compress 2^30 (50 % dense) | block_mkperm 2^26 keys x 4096 buckets | scatter_add f32 2^28 -> 2^20 bins
+
+value = algorithmic bytes of the whole suite / device time of one step (GB/s), inputs larger
+than L2 (no flush needed). With --gpus N the same TOTAL arrays are sharded over N ranks
+("strong" scaling); NCCL is used only for the combine messages.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
+
+--impl reference times the reference's own CPU implementation of the path (the unmodified
+drjit-core LLVM-backend primitives built into oracle/_ref) on the host cores.
+--scale S shrinks every array by 2^S (debugging only; the JSON says so).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "achieved HBM GB/s & % peak: reduce/scan/compress/mkperm @2^28, 1/2/4/8 GPU"
+
+# name -> (log2 elements, algorithmic bytes per element)   [SURVEY.md section 8d / BASELINE.md 2c]
+SUITE = [
+    ("sum_f32", 28, 4.0),
+    ("block_reduce256_f32", 28, 4.0 + 4.0 / 256),
+    ("dot_f32", 28, 8.0),
+    ("prefix_sum_u32", 30, 8.0),
+    ("compress_u8", 30, 3.0),          # 1 + 4 * density, density = 0.5
+    ("mkperm_4096", 26, 12.0),
+    ("scatter_add_f32", 28, 8.0),
+]
+BINS_LOG2 = 20
+BUCKETS = 4096
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+#  clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                self.samples.append((float(parts[0]), float(parts[1])))
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+#  reference arm: the unmodified reference's CPU primitives (oracle/_ref), all host threads
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_log2):
+    """Times the suite on a bounded sample (2^sample_log2 elements per primitive, 2^(sample-2)
+    for mkperm) with the reference LLVM backend. Returns (GB/s, per-primitive dict, cores)."""
+    import numpy as np
+    from oracle import capi, ref
+
+    cores = os.cpu_count() or 1
+    L = ref.lib(cuda=False, llvm=True)
+    L.ref_llvm_set_thread_count(cores)
+    n = 1 << sample_log2
+    nk = 1 << max(10, sample_log2 - 2)
+    x = capi.unit_f32(n); y = capi.unit_f32(n, xor=0x9E3779B9)
+    u = capi.fmix32(n); m = capi.mask_u8(n, 128); keys = capi.fmix32(nk, mask=BUCKETS - 1)
+
+    import ctypes
+    vp = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(vp)  # noqa: E731
+    out_f = np.zeros(max(1, n // 256), np.float32); out_u = np.empty(n, np.uint32)
+    idx = np.empty(n, np.uint32); perm = np.empty(nk, np.uint32); offs = np.zeros(4 * BUCKETS + 1, np.uint32)
+    dot_out = np.zeros(1, np.float32)
+    VT_F32, VT_U32, ADD, LLVM = 14, 8, 1, 2
+
+    prims = {
+        "sum_f32": (n * 4.0, lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, n, P(x), P(out_f)), L.ref_sync())),
+        "block_reduce256_f32": (n * (4.0 + 4.0 / 256), lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, 256, P(x), P(out_f)), L.ref_sync())),
+        "dot_f32": (n * 8.0, lambda: L.ref_reduce_dot(LLVM, VT_F32, P(x), P(y), n, P(dot_out))),
+        "prefix_sum_u32": (n * 8.0, lambda: (L.ref_block_prefix_reduce(LLVM, VT_U32, ADD, n, n, 1, 0, P(u), P(out_u)), L.ref_sync())),
+        "compress_u8": (n * 3.0, lambda: L.ref_compress(LLVM, P(m), n, P(idx))),
+        "mkperm_4096": (nk * 12.0, lambda: (L.ref_block_mkperm(LLVM, P(keys), nk, nk, BUCKETS, P(perm), P(offs)), L.ref_sync())),
+        # scatter_add: the reference CPU path needs its LLVM JIT (ReduceMode::Expand), which the
+        # stub libLLVM cannot provide -> reported as n/a and left out of the CPU aggregate.
+    }
+    times = {k: [] for k in prims}
+    for it in range(warmup + steps):
+        for name, (_, fn) in prims.items():
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times[name].append(dt)
+    per = {}
+    tot_bytes = tot_time = 0.0
+    for name, (nbytes, _) in prims.items():
+        t = sum(times[name]) / len(times[name])
+        per[name] = {"GBps": nbytes / t / 1e9, "ms": t * 1e3}
+        tot_bytes += nbytes; tot_time += t
+    per["scatter_add_f32"] = "n/a (reference CPU scatter needs the LLVM JIT)"
+    return tot_bytes / tot_time / 1e9, per, cores, tot_time
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_log2 = 26
+    value, per, cores, step_s = cpu_reference_run(args.steps, max(1, min(args.warmup, 2)), sample_log2)
+    sample = (f"suite without scatter_add at 2^{sample_log2} elements per primitive (mkperm 2^{sample_log2 - 2} keys), "
+              f"host arrays, unmodified reference LLVM-backend primitives, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "primitives": per, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "primitive suite: sum/block_reduce(256)/dot f32 2^28, exclusive prefix_sum u32 2^30, "
+                        "compress u8 2^30 (50%), block_mkperm 2^26 x 4096 buckets, scatter_add f32 2^28 -> 2^20 bins",
+            "sharding": f"contiguous index ranges over {args.gpus} rank(s), NCCL only for combine messages",
+            "l2": "every input array > 126 MB L2 (no flush needed)",
+            "scale_shift": args.scale}
+
+
+# ------------------------------------------------------------------------------------------
+#  GPU arm
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=0, help="shrink every array by 2^SCALE (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import drjit_b200 as dr
+    from drjit_b200 import ReduceOp, VarType, ops
+    from drjit_b200 import dist as ddist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sh = ddist.Sharded(rank=rank, world=world, group=dist.group.WORLD if world > 1 else None)
+
+    peak, peak_src = measured_peaks()
+    S = args.scale
+    size = {name: 1 << (lg - S) for name, lg, _ in SUITE}
+    bpe = {name: b for name, _, b in SUITE}
+    bins = 1 << max(4, BINS_LOG2 - S)
+
+    # ---- shard-resident synthetic inputs (generated on the device) -------------------------
+    def shard(n, align=1024):
+        return sh.shard_range(n, align)
+
+    lo_f, hi_f = shard(size["sum_f32"])
+    x = torch.empty(hi_f - lo_f, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1, start=lo_f)
+    y = torch.empty(hi_f - lo_f, dtype=torch.float32, device=dev); ops.fill_fmix32(y, 1, start=lo_f, xor=0x9E3779B9)
+    lo_u, hi_u = shard(size["prefix_sum_u32"])
+    u = torch.empty(hi_u - lo_u, dtype=torch.int32, device=dev); ops.fill_fmix32(u, 0, start=lo_u)
+    u_out = torch.empty_like(u)
+    lo_m, hi_m = shard(size["compress_u8"])
+    mask = torch.empty(hi_m - lo_m, dtype=torch.uint8, device=dev); ops.fill_fmix32(mask, 2, start=lo_m, and_=128)
+    c_out = torch.empty(hi_m - lo_m, dtype=torch.int32, device=dev)
+    lo_k, hi_k = shard(size["mkperm_4096"])
+    keys = torch.empty(hi_k - lo_k, dtype=torch.int32, device=dev); ops.fill_fmix32(keys, 0, start=lo_k, and_=BUCKETS - 1)
+    perm = torch.empty_like(keys)
+    lo_s, hi_s = shard(size["scatter_add_f32"])
+    sidx = torch.empty(hi_s - lo_s, dtype=torch.int32, device=dev); ops.fill_fmix32(sidx, 0, start=lo_s, xor=0x85EBCA6B, and_=bins - 1)
+    sval = x if (lo_s, hi_s) == (lo_f, hi_f) else torch.empty(hi_s - lo_s, dtype=torch.float32, device=dev)
+    if sval is not x:
+        ops.fill_fmix32(sval, 1, start=lo_s)
+    bins_t = torch.zeros(bins, dtype=torch.float32, device=dev)
+    br_out = torch.empty((x.numel() + 255) // 256, dtype=torch.float32, device=dev)
+
+    results = {}
+
+    def p_sum():
+        results["sum"] = sh.reduce(ReduceOp.Add, x)
+
+    def p_block_reduce():
+        results["br"] = ops.block_reduce(ReduceOp.Add, x, 256, out=br_out)   # block-aligned shards: no exchange
+
+    def p_dot():
+        results["dot"] = sh.dot(x, y)
+
+    def p_prefix():
+        results["scan"] = sh.prefix_sum(u, vt=VarType.UInt32, out=u_out)
+
+    def p_compress():
+        results["count"] = sh.compress(mask, lo_m, out=c_out)
+
+    def p_mkperm():
+        results["mkperm"] = sh.mkperm(keys, BUCKETS, lo_k, perm=perm)
+
+    def p_scatter():
+        bins_t.zero_()
+        results["bins"] = sh.scatter_add(bins_t, sval, sidx)
+
+    prims = [("sum_f32", p_sum), ("block_reduce256_f32", p_block_reduce), ("dot_f32", p_dot),
+             ("prefix_sum_u32", p_prefix), ("compress_u8", p_compress), ("mkperm_4096", p_mkperm),
+             ("scatter_add_f32", p_scatter)]
+    total_bytes = sum(size[n] * bpe[n] for n, _ in prims)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(events=None):
+        for i, (name, fn) in enumerate(prims):
+            if events is not None:
+                events[i][0].record()
+            fn()
+            if events is not None:
+                events[i][1].record()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dr.launch_count(reset=True)
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prims]
+          for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for k in range(args.steps):
+        one_step(ev[k])
+    end.record()
+    barrier()
+    launches = dr.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = start.elapsed_time(end)
+    per_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps
+              for i in range(len(prims))]
+    t = torch.tensor([total_ms] + per_ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0]); per_ms = [float(v) for v in t[1:]]
+    ms_per_step = total_ms / args.steps
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+
+    primitives = {}
+    for (name, _), ms in zip(prims, per_ms):
+        gbs = size[name] * bpe[name] / (ms * 1e-3) / 1e9
+        primitives[name] = {"elements": size[name], "ms": round(ms, 4), "GBps": round(gbs, 1),
+                            "Gelem_per_s": round(size[name] / (ms * 1e-3) / 1e9, 2),
+                            "frac_of_peak_per_gpu": round(gbs / (peak * world), 4)}
+
+    # ---- end-to-end: host buffers through the public API, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank,
+                      dict(x=x, y=y, u=u, mask=mask, keys=keys, sidx=sidx, sval=sval),
+                      dict(u_out=u_out, c_out=c_out, perm=perm, bins_t=bins_t, br_out=br_out),
+                      prims, results, total_bytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # dominant kernel for the roofline object: the single-pass scan (largest share of the step)
+    scan = primitives["prefix_sum_u32"]
+    roofline = {"bound": "hbm", "kernel": "prefix_reduce_kernel<u32,Add> (exclusive prefix_sum, 2^30/N elements per rank)",
+                "achieved": scan["GBps"] / world, "peak": peak, "unit": "GB/s",
+                "frac": round(scan["GBps"] / world / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": size["prefix_sum_u32"] * 8.0 / world}
+
+    cpu_baseline = None
+    if not args.no_cpu:
+        try:
+            v, per, cores, _ = cpu_reference_run(2, 1, 24)
+            cpu_baseline = {"value": round(v, 2), "unit": "GB/s", "cores": cores, "kind": "reference",
+                            "sample": "suite without scatter_add at 2^24 elements per primitive (mkperm 2^22 keys), "
+                                      "unmodified reference LLVM-backend CPU primitives (oracle/_ref), all host threads",
+                            "primitives": {k: (round(p["GBps"], 2) if isinstance(p, dict) else p) for k, p in per.items()}}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
+                            "sample": f"unavailable: {e}"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
+        "config": workload_config(args), "frac_of_hbm_peak": round(value / (peak * world), 4),
+        "primitives": primitives, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, prims, results, total_bytes):
+    """Same suite, but every step first copies the step's inputs host->device from pinned
+    memory and afterwards reads every primitive's result back to the host."""
+    host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in inputs.items() if k != "sval" or v is not inputs["x"]}
+    for k, h in host_in.items():
+        h.copy_(inputs[k])
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outputs.items()}
+    h2d = sum(h.numel() * h.element_size() for h in host_in.values())
+    steps = max(2, min(args.steps, 3))
+
+    def step():
+        for k, h in host_in.items():
+            inputs[k].copy_(h, non_blocking=True)
+        for _, fn in prims:
+            fn()
+        d2h = 0
+        count = results["count"][1][rank]
+        for k, v in outputs.items():
+            if k == "c_out":
+                host_out[k][:count].copy_(v[:count], non_blocking=True); d2h += count * 4
+            else:
+                host_out[k].copy_(v, non_blocking=True); d2h += v.numel() * v.element_size()
+        for k in ("sum", "dot"):
+            results[k].cpu(); d2h += 4
+        return d2h
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(steps):
+        d2h = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    return {"value": round(total_bytes / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": int(h2d) * world,
+            "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "note": "per rank: pinned host inputs -> device, suite through the public API, every result "
+                    "(scalars, block sums, scan, index list, permutation, bins) -> pinned host"}
+
+
+if __name__ == "__main__":
+    main()

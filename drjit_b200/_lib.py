@@ -1,0 +1,69 @@
+"""ctypes binding of ``lib/libdrjit_b200.so`` (the C ABI declared in ``include/drjit_b200.h``).
+
+The product path has no fallback: if the shared library is missing this module raises
+at import time, and every call fails loudly when the CUDA device is unusable.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdrjit_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA library first "
+        "(`python -c 'import __graft_entry__ as g; g.build()'` or `make -C drjit_b200/csrc`). "
+        "drjit_b200 has no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+vp, u32, u64, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+pu32, pint = ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); mirrors include/drjit_b200.h one to one
+SIGNATURES = {
+    "drjit_b200_last_error": (ctypes.c_char_p, []),
+    "drjit_b200_version": (ctypes.c_char_p, []),
+    "drjit_b200_init": (i32, []),
+    "drjit_b200_shutdown": (i32, []),
+    "drjit_b200_set_allocator": (i32, [vp, vp, vp]),
+    "drjit_b200_launch_count": (u64, [i32]),
+    "drjit_b200_memset_async": (i32, [vp, vp, u32, u32, vp]),
+    "drjit_b200_block_reduce": (i32, [vp, i32, i32, u32, u32, vp, vp]),
+    "drjit_b200_block_reduce_bool": (i32, [vp, vp, u32, vp, i32]),
+    "drjit_b200_all": (i32, [vp, vp, u32, pint]),
+    "drjit_b200_any": (i32, [vp, vp, u32, pint]),
+    "drjit_b200_reduce_dot": (i32, [vp, i32, vp, vp, u32, vp]),
+    "drjit_b200_block_prefix_reduce": (i32, [vp, i32, i32, u32, u32, i32, i32, vp, vp]),
+    "drjit_b200_compress": (i32, [vp, vp, u32, vp, pu32]),
+    "drjit_b200_block_mkperm": (i32, [vp, vp, u32, u32, u32, vp, vp, pu32]),
+    "drjit_b200_poke": (i32, [vp, vp, vp, u32]),
+    "drjit_b200_aggregate": (i32, [vp, vp, vp, u32]),
+    "drjit_b200_scatter_reduce": (i32, [vp, i32, i32, i32, vp, u32, vp, vp, vp, u32]),
+    "drjit_b200_prefix_reduce_carry": (i32, [vp, i32, i32, u32, i32, i32, vp, vp, vp, vp]),
+    "drjit_b200_compress_async": (i32, [vp, vp, u32, u32, vp, vp]),
+    "drjit_b200_mkperm_sharded": (i32, [vp, vp, u32, u32, u32, vp, vp]),
+    "drjit_b200_fill_fmix32": (i32, [vp, i32, vp, u64, u64, u32, u32]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the library does not export the header's symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+OK, EINVAL, EUNSUPPORTED, ECUDA, EFATAL = 0, -1, -2, -3, -4
+
+
+class FatalError(RuntimeError):
+    """The reference would call jitc_fail() -> abort() here (CUDA error, bucket_count == 0 ...)."""
+
+
+def check(status):
+    """Map a status code to the exception the reference surfaces in Python:
+    jitc_raise() -> std::runtime_error -> RuntimeError; jitc_fail() -> abort()."""
+    if status == OK:
+        return
+    msg = lib.drjit_b200_last_error().decode()
+    if status in (EINVAL, EUNSUPPORTED):
+        raise RuntimeError(msg)
+    raise FatalError(msg)

@@ -1,0 +1,536 @@
+/*
+ * block_reduce.cu -- block reductions, full reductions and dot products.
+ *
+ * Replaces CUDAThreadState::block_reduce (ext/drjit-core/src/cuda_ts.cpp:195-352) with its
+ * 310 precompiled `block_reduce_*` kernels (resources/block_reduce.cuh:83-273), and
+ * CUDAThreadState::reduce_dot (cuda_ts.cpp:354-398, resources/reduce_2.cuh:12-76).
+ *
+ * Design (HBM-bound, read-once):
+ *  - "group" kernel for blocks up to 4 KiB: G = 1..32 lanes cooperate on one block, each lane
+ *    keeps four 128-bit loads in flight, the result is combined with a G-wide butterfly
+ *    (redux.sync for 32-bit integers) -- every block size, vectorised whenever rows are
+ *    16-byte aligned (the reference vectorises only block_size >= 1024, cuda_ts.cpp:264-269).
+ *  - "chunk" kernel for larger blocks and full reductions: each CTA streams one contiguous
+ *    chunk with 4 x 128-bit loads per thread in flight (head/tail peeled, so any element-
+ *    aligned pointer is vectorised), writes one partial, and the last CTA to arrive for a
+ *    block combines the partials in a fixed order. One launch, no temporary allocation,
+ *    deterministic; the reference recurses with 2-3 launches and temp buffers (:347-351).
+ */
+#include "common.cuh"
+#include "runtime.h"
+
+namespace djb {
+
+constexpr uint32_t kThreads = 256;
+
+// ---------------------------------------------------------------------------
+//  Group kernel
+// ---------------------------------------------------------------------------
+template <typename T, typename Op, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+block_reduce_group_kernel(const T *__restrict__ in, T *__restrict__ out, uint32_t size,
+                          uint32_t block_size, uint32_t block_count, uint32_t log2_g) {
+    using A = acc_t<T>;
+    constexpr uint32_t V = VEC ? 16 / sizeof(T) : 1;
+    const A ident = Op::template identity<A>();
+
+    const uint32_t G = 1u << log2_g,
+                   groups_per_cta = kThreads >> log2_g,
+                   gl = threadIdx.x & (G - 1),
+                   total_groups = gridDim.x * groups_per_cta;
+
+    // Uniform trip count per warp: shuffles below need all 32 lanes
+    const uint32_t first_group_of_warp = blockIdx.x * groups_per_cta + ((threadIdx.x & ~31u) >> log2_g);
+    const uint32_t my_group_offset = ((threadIdx.x & 31u) >> log2_g);
+
+    for (uint64_t wb = first_group_of_warp; wb < block_count; wb += total_groups) {
+        const uint64_t b = wb + my_group_offset;
+        const bool valid = b < block_count;
+        const uint64_t start = b * block_size;
+        uint64_t end = start + block_size;
+        if (end > size) end = size;
+        if (!valid) end = 0;
+
+        A acc = ident;
+        const uint64_t step = (uint64_t) G * V;
+        for (uint64_t base = start + (uint64_t) gl * V; base < end; base += 4 * step) {
+            if constexpr (VEC) {
+                Vec16<T> tmp[4];
+                bool ok[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t idx = base + u * step;
+                    ok[u] = idx < end;
+                    if (ok[u]) tmp[u] = ld_stream<T>(in + idx);
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ok[u]) {
+                        #pragma unroll
+                        for (uint32_t e = 0; e < V; ++e)
+                            acc = Op::template apply<A>(acc, to_acc<A>(tmp[u].v[e]));
+                    }
+                }
+            } else {
+                T tmp[4];
+                bool ok[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t idx = base + u * step;
+                    ok[u] = idx < end;
+                    if (ok[u]) tmp[u] = __ldg(in + idx);
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) acc = Op::template apply<A>(acc, to_acc<A>(tmp[u]));
+            }
+        }
+
+        if (log2_g == 5) {
+            acc = WarpReduce<Op, A>::template run<32>(acc);
+        } else {
+            for (uint32_t m = G >> 1; m > 0; m >>= 1)
+                acc = Op::template apply<A>(acc, shfl_xor(acc, m));
+        }
+
+        if (gl == 0 && valid)
+            out[b] = from_acc<T>(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------
+//  Chunk kernel (also the dot product when DOT)
+// ---------------------------------------------------------------------------
+template <typename T, typename Op, bool DOT> struct ChunkAccum {
+    using A = acc_t<T>;
+    static __device__ __forceinline__ A elem(A acc, T a, T b) {
+        if constexpr (DOT) {
+            if constexpr (sizeof(A) == 8) return fma((A) a, (A) b, acc);
+            else return fmaf(to_acc<A>(a), to_acc<A>(b), acc);
+        } else {
+            (void) b;
+            return Op::template apply<A>(acc, to_acc<A>(a));
+        }
+    }
+};
+
+template <typename T, typename Op, bool DOT, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+block_reduce_chunk_kernel(const T *__restrict__ in, const T *__restrict__ in2, T *__restrict__ out,
+                          acc_t<T> *__restrict__ partials, uint32_t *__restrict__ counters,
+                          uint32_t size, uint32_t block_size, uint32_t chunk_elems,
+                          uint32_t chunks_per_block) {
+    using A = acc_t<T>;
+    using Acc = ChunkAccum<T, Op, DOT>;
+    constexpr uint32_t V = 16 / sizeof(T);
+    const A ident = Op::template identity<A>();
+    __shared__ A smem[32];
+    __shared__ uint32_t is_last_smem;
+
+    const uint32_t block = blockIdx.x / chunks_per_block,
+                   chunk = blockIdx.x - block * chunks_per_block;
+    const uint64_t block_start = (uint64_t) block * block_size;
+    uint64_t start = block_start + (uint64_t) chunk * chunk_elems,
+             end = block_start + min((uint64_t) (chunk + 1) * chunk_elems, (uint64_t) block_size);
+    if (end > size) end = size;
+    if (start > end) start = end;
+
+    A acc = ident;
+    const uint32_t tid = threadIdx.x;
+
+    if constexpr (VEC) {
+        // Peel scalars up to the first 16-byte boundary, vectorise the body, peel the tail
+        const uintptr_t addr = (uintptr_t) (in + start);
+        uint64_t head = ((16 - (addr & 15)) & 15) / sizeof(T);
+        if (head > end - start) head = end - start;
+        const uint64_t body_start = start + head,
+                       nvec = (end - body_start) / V,
+                       tail_start = body_start + nvec * V;
+
+        if (tid < head)
+            acc = Acc::elem(acc, in[start + tid], DOT ? in2[start + tid] : T());
+        if (tid < end - tail_start)
+            acc = Acc::elem(acc, in[tail_start + tid], DOT ? in2[tail_start + tid] : T());
+
+        const Vec16<T> *vin = reinterpret_cast<const Vec16<T> *>(in + body_start);
+        const Vec16<T> *vin2 = reinterpret_cast<const Vec16<T> *>(in2 + body_start);
+        for (uint64_t base = tid; base < nvec; base += 4 * kThreads) {
+            Vec16<T> ta[4], tb[4];
+            bool ok[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t idx = base + u * kThreads;
+                ok[u] = idx < nvec;
+                if (ok[u]) {
+                    ta[u] = ld_stream<T>(vin + idx);
+                    if constexpr (DOT) tb[u] = ld_stream<T>(vin2 + idx);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ok[u]) {
+                    #pragma unroll
+                    for (uint32_t e = 0; e < V; ++e)
+                        acc = Acc::elem(acc, ta[u].v[e], DOT ? tb[u].v[e] : T());
+                }
+            }
+        }
+    } else {
+        for (uint64_t base = start + tid; base < end; base += 4 * kThreads) {
+            T ta[4], tb[4];
+            bool ok[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t idx = base + u * kThreads;
+                ok[u] = idx < end;
+                if (ok[u]) {
+                    ta[u] = __ldg(in + idx);
+                    if constexpr (DOT) tb[u] = __ldg(in2 + idx);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) acc = Acc::elem(acc, ta[u], DOT ? tb[u] : T());
+        }
+    }
+
+    // Partial sums are *added* regardless of Op when computing a dot product
+    using Comb = std::conditional_t<DOT, OpAdd, Op>;
+    A total = block_reduce<Comb, A, kThreads>(acc, smem, ident);
+
+    if (chunks_per_block == 1) {
+        if (tid == 0) out[block] = from_acc<T>(total);
+        return;
+    }
+
+    // Publish the partial; the last CTA of this block folds all of them in a fixed order
+    if (tid == 0) {
+        partials[blockIdx.x] = total;
+        __threadfence();
+        const uint32_t prev = atomicAdd(&counters[block], 1u);
+        is_last_smem = prev == chunks_per_block - 1;
+    }
+    __syncthreads();
+    if (!is_last_smem)
+        return;
+    __threadfence();
+
+    const volatile A *p = partials + (uint64_t) block * chunks_per_block;
+    acc = ident;
+    for (uint32_t j = tid; j < chunks_per_block; j += kThreads)
+        acc = Comb::template apply<A>(acc, p[j]);
+    __syncthreads(); // smem reuse
+    total = block_reduce<Comb, A, kThreads>(acc, smem, ident);
+    if (tid == 0) {
+        out[block] = from_acc<T>(total);
+        counters[block] = 0; // leave the control block zeroed for the next call
+    }
+}
+
+// ---------------------------------------------------------------------------
+//  Host side
+// ---------------------------------------------------------------------------
+constexpr uint32_t kGroupMaxBytes = 4096;     // blocks up to this size use the group kernel
+constexpr uint32_t kMinChunkBytes = 32768;    // never split a block into chunks smaller than this
+constexpr uint32_t kCtasPerSm = 8;
+
+template <typename T, typename Op>
+static void launch_block_reduce(cudaStream_t stream, uint32_t size, uint32_t block_size,
+                                const void *in_, void *out_) {
+    using A = acc_t<T>;
+    const T *in = (const T *) in_;
+    T *out = (T *) out_;
+    const DeviceProps &dev = device_props();
+    const uint32_t block_count = ceil_div(size, block_size);
+    const uint64_t block_bytes = (uint64_t) block_size * sizeof(T);
+    constexpr uint32_t V = 16 / sizeof(T);
+
+    if (block_bytes <= kGroupMaxBytes) {
+        const bool vec = block_size % V == 0 && size % V == 0 && ((uintptr_t) in % 16) == 0;
+        const uint32_t units = vec ? block_size / V : block_size;      // loads per block
+        uint32_t log2_g = 0;
+        while ((1u << log2_g) < 32 && (4u << log2_g) < units)
+            ++log2_g;
+        const uint32_t groups_per_cta = kThreads >> log2_g;
+        uint32_t grid = ceil_div(block_count, groups_per_cta);
+        const uint32_t max_grid = dev.sm_count * kCtasPerSm * 4;
+        if (grid > max_grid) grid = max_grid;
+        if (vec)
+            block_reduce_group_kernel<T, Op, true><<<grid, kThreads, 0, stream>>>(
+                in, out, size, block_size, block_count, log2_g);
+        else
+            block_reduce_group_kernel<T, Op, false><<<grid, kThreads, 0, stream>>>(
+                in, out, size, block_size, block_count, log2_g);
+        DJB_POST_LAUNCH();
+        return;
+    }
+
+    // Chunk kernel: split blocks so that ~kCtasPerSm CTAs per SM are busy
+    const uint32_t target_ctas = dev.sm_count * kCtasPerSm;
+    uint32_t cpb = 1;
+    if (block_count < target_ctas) {
+        cpb = ceil_div(target_ctas, block_count);
+        const uint32_t max_cpb = (uint32_t) std::max<uint64_t>(1, block_bytes / kMinChunkBytes);
+        if (cpb > max_cpb) cpb = max_cpb;
+    }
+    // chunk size: multiple of a full CTA iteration so that only the last chunk has a ragged end
+    const uint32_t quantum = kThreads * V * 4;
+    uint32_t chunk_elems = ceil_div(ceil_div(block_size, cpb), quantum) * quantum;
+    if (chunk_elems < quantum) chunk_elems = quantum;
+    cpb = ceil_div(block_size, chunk_elems);
+
+    Scratch scratch(stream);
+    A *partials = nullptr;
+    uint32_t *counters = nullptr;
+    if (cpb > 1) {
+        if (block_count > Scratch::kZeroedCounters)
+            raise(DRJIT_B200_EFATAL, "jit_block_reduce(): internal error (counter overflow)");
+        partials = (A *) scratch.device((size_t) block_count * cpb * sizeof(A));
+        counters = scratch.zeroed_counters();
+    }
+    const uint64_t grid = (uint64_t) block_count * cpb;
+    block_reduce_chunk_kernel<T, Op, false, true><<<(uint32_t) grid, kThreads, 0, stream>>>(
+        in, nullptr, out, partials, counters, size, block_size, chunk_elems, cpb);
+    DJB_POST_LAUNCH();
+}
+
+template <typename T> static void dispatch_op_int(cudaStream_t s, int op, uint32_t size,
+                                                  uint32_t bs, const void *in, void *out) {
+    switch (op) {
+        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_AND: launch_block_reduce<T, OpAnd>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_OR:  launch_block_reduce<T, OpOr>(s, size, bs, in, out); break;
+        default: raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): unsupported reduction type!");
+    }
+}
+
+template <typename T> static void dispatch_op_minmax(cudaStream_t s, int op, uint32_t size,
+                                                     uint32_t bs, const void *in, void *out) {
+    switch (op) {
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
+        default: raise(DRJIT_B200_EFATAL, "jit_block_reduce(): internal dispatch error");
+    }
+}
+
+template <typename T> static void dispatch_op_float(cudaStream_t s, int vt, int op, uint32_t size,
+                                                    uint32_t bs, const void *in, void *out) {
+    switch (op) {
+        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
+        default:
+            // wording of cuda_ts.cpp:313-315
+            raise(DRJIT_B200_EUNSUPPORTED,
+                  "jit_block_reduce(): no existing kernel for type=%s, op=%s!", type_name(vt),
+                  op_name(op));
+    }
+}
+
+void block_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uint32_t block_size,
+                  const void *in, void *out) {
+    if (size == 0)
+        return;
+    if (block_size == 0 || block_size > size) // cuda_ts.cpp:203-207 (reference text says "prefix")
+        raise(DRJIT_B200_EINVAL,
+              "jit_block_reduce(): invalid block size (size=%u, block_size=%u)!", size, block_size);
+
+    const uint32_t tsize = type_size(vt);
+    if (tsize == 0 || op < DRJIT_B200_OP_ADD || op > DRJIT_B200_OP_OR)
+        raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): no existing kernel for type=%s, op=%s!",
+              type_name(vt), op_name(op));
+
+    if (block_size == 1) { // cuda_ts.cpp:210-213
+        if (in != out)
+            DJB_CUDA_CHECK(cudaMemcpyAsync(out, in, (size_t) size * tsize, cudaMemcpyDeviceToDevice, stream));
+        return;
+    }
+
+    // Signed sum/product/and/or reductions can use the unsigned kernel (cuda_ts.cpp:215-225)
+    const bool sign_agnostic = op == DRJIT_B200_OP_ADD || op == DRJIT_B200_OP_MUL ||
+                               op == DRJIT_B200_OP_AND || op == DRJIT_B200_OP_OR;
+    switch (vt) {
+        case DRJIT_B200_VT_BOOL:
+        case DRJIT_B200_VT_UINT8:  dispatch_op_int<uint8_t>(stream, op, size, block_size, in, out); break;
+        case DRJIT_B200_VT_UINT32: dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out); break;
+        case DRJIT_B200_VT_UINT64: dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out); break;
+        case DRJIT_B200_VT_INT32:
+            if (sign_agnostic) dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out);
+            else dispatch_op_minmax<int32_t>(stream, op, size, block_size, in, out);
+            break;
+        case DRJIT_B200_VT_INT64:
+            if (sign_agnostic) dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out);
+            else dispatch_op_minmax<int64_t>(stream, op, size, block_size, in, out);
+            break;
+        case DRJIT_B200_VT_FLOAT16: dispatch_op_float<__half>(stream, vt, op, size, block_size, in, out); break;
+        case DRJIT_B200_VT_FLOAT32: dispatch_op_float<float>(stream, vt, op, size, block_size, in, out); break;
+        case DRJIT_B200_VT_FLOAT64: dispatch_op_float<double>(stream, vt, op, size, block_size, in, out); break;
+        default:
+            raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): no existing kernel for type=%s, op=%s!",
+                  type_name(vt), op_name(op));
+    }
+}
+
+// ---------------------------------------------------------------------------
+//  dr.all / dr.any (src/init.cpp:919-939, src/util.cpp:153-211)
+// ---------------------------------------------------------------------------
+/// Reduces a bool array with And/Or into four packed bytes. The reference pads the caller's
+/// buffer with the identity and reduces it as u32; here the ragged tail is folded in by the
+/// kernel itself so nothing is written past values[size).
+__global__ void __launch_bounds__(kThreads)
+reduce_bool_kernel(const uint8_t *__restrict__ values, uint32_t size, uint32_t *__restrict__ partials,
+                   uint32_t *__restrict__ counters, uint8_t *__restrict__ out, int is_and) {
+    __shared__ uint32_t smem[32];
+    __shared__ uint32_t is_last_smem;
+    const uint32_t ident = is_and ? 0xffffffffu : 0u;
+    uint32_t acc = ident;
+
+    const uintptr_t addr = (uintptr_t) values;
+    uint64_t head = (16 - (addr & 15)) & 15;
+    if (head > size) head = size;
+    const uint64_t nvec = (size - head) / 16, tail_start = head + nvec * 16;
+    const uint64_t gtid = (uint64_t) blockIdx.x * kThreads + threadIdx.x,
+                   gstride = (uint64_t) gridDim.x * kThreads;
+
+    auto fold_byte = [&](uint8_t b) {
+        // replicate into all four bytes: the position inside the packed word is irrelevant
+        const uint32_t w = b * 0x01010101u;
+        acc = is_and ? (acc & w) : (acc | w);
+    };
+    if (gtid < head) fold_byte(values[gtid]);
+    if (gtid < size - tail_start) fold_byte(values[tail_start + gtid]);
+
+    const Vec16<uint32_t> *vin = reinterpret_cast<const Vec16<uint32_t> *>(values + head);
+    for (uint64_t base = gtid; base < nvec; base += 4 * gstride) {
+        Vec16<uint32_t> t[4];
+        bool ok[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = base + u * gstride < nvec;
+            if (ok[u]) t[u] = ld_stream<uint32_t>(vin + base + u * gstride);
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) {
+                #pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    acc = is_and ? (acc & t[u].v[e]) : (acc | t[u].v[e]);
+            }
+    }
+
+    uint32_t total = is_and ? block_reduce<OpAnd, uint32_t, kThreads>(acc, smem, ident)
+                            : block_reduce<OpOr, uint32_t, kThreads>(acc, smem, ident);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = total;
+        __threadfence();
+        is_last_smem = atomicAdd(counters, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last_smem)
+        return;
+    __threadfence();
+    acc = ident;
+    const volatile uint32_t *p = partials;
+    for (uint32_t j = threadIdx.x; j < gridDim.x; j += kThreads)
+        acc = is_and ? (acc & p[j]) : (acc | p[j]);
+    __syncthreads();
+    total = is_and ? block_reduce<OpAnd, uint32_t, kThreads>(acc, smem, ident)
+                   : block_reduce<OpOr, uint32_t, kThreads>(acc, smem, ident);
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<uint32_t *>(out) = total; // four packed bools, like the reference's u32 reduce
+        *counters = 0;
+    }
+}
+
+static void launch_reduce_bool(cudaStream_t stream, Scratch &scratch, const uint8_t *values,
+                               uint32_t size, uint8_t *out, int op) {
+    const DeviceProps &dev = device_props();
+    uint32_t grid = ceil_div(size, kThreads * 64);
+    grid = std::max(1u, std::min(grid, dev.sm_count * kCtasPerSm));
+    uint32_t *partials = (uint32_t *) scratch.device(grid * sizeof(uint32_t));
+    reduce_bool_kernel<<<grid, kThreads, 0, stream>>>(values, size, partials, scratch.zeroed_counters(),
+                                                      out, op == DRJIT_B200_OP_AND);
+    DJB_POST_LAUNCH();
+}
+
+void block_reduce_bool(cudaStream_t stream, const uint8_t *values, uint32_t size, uint8_t *out, int op) {
+    if (op != DRJIT_B200_OP_AND && op != DRJIT_B200_OP_OR)
+        raise(DRJIT_B200_EINVAL, "jit_block_reduce_bool(): op must be And or Or!");
+    if (((uintptr_t) out % 4) != 0)
+        raise(DRJIT_B200_EINVAL, "jit_block_reduce_bool(): output must be 4-byte aligned!");
+    Scratch scratch(stream);
+    if (size == 0) { // reduction over nothing = identity
+        const uint32_t ident = op == DRJIT_B200_OP_AND ? 0x01010101u : 0u;
+        DJB_CUDA_CHECK(cudaMemcpyAsync(out, &ident, 4, cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    launch_reduce_bool(stream, scratch, values, size, out, op);
+}
+
+bool all_any(cudaStream_t stream, const uint8_t *values, uint32_t size, int op) {
+    if (size == 0)
+        return op == DRJIT_B200_OP_AND;
+    Scratch scratch(stream);
+    uint32_t *pinned = scratch.pinned_words();
+    uint8_t *dev_view = nullptr;
+    DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &dev_view, pinned, 0));
+    launch_reduce_bool(stream, scratch, values, size, dev_view, op);
+    DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(pinned);
+    // util.cpp:191,207: combine the four packed partials
+    return op == DRJIT_B200_OP_AND ? (b[0] & b[1] & b[2] & b[3]) != 0 : (b[0] | b[1] | b[2] | b[3]) != 0;
+}
+
+// ---------------------------------------------------------------------------
+//  Dot product
+// ---------------------------------------------------------------------------
+template <typename T>
+static void launch_reduce_dot(cudaStream_t stream, const void *a_, const void *b_, uint32_t size, void *out_) {
+    using A = acc_t<T>;
+    constexpr uint32_t V = 16 / sizeof(T);
+    const T *a = (const T *) a_, *b = (const T *) b_;
+    T *out = (T *) out_;
+    const DeviceProps &dev = device_props();
+
+    const uint64_t bytes = (uint64_t) size * sizeof(T);
+    uint32_t cpb = dev.sm_count * kCtasPerSm;
+    const uint32_t max_cpb = (uint32_t) std::max<uint64_t>(1, bytes / (kMinChunkBytes / 2));
+    if (cpb > max_cpb) cpb = max_cpb;
+    const uint32_t quantum = kThreads * V * 4;
+    uint32_t chunk_elems = ceil_div(ceil_div(size, cpb), quantum) * quantum;
+    cpb = ceil_div(size, chunk_elems);
+
+    Scratch scratch(stream);
+    A *partials = cpb > 1 ? (A *) scratch.device((size_t) cpb * sizeof(A)) : nullptr;
+    uint32_t *counters = scratch.zeroed_counters();
+    // both streams must share their misalignment for the 128-bit path
+    const bool vec = (((uintptr_t) a ^ (uintptr_t) b) & 15) == 0;
+    if (vec)
+        block_reduce_chunk_kernel<T, OpAdd, true, true><<<cpb, kThreads, 0, stream>>>(
+            a, b, out, partials, counters, size, size, chunk_elems, cpb);
+    else
+        block_reduce_chunk_kernel<T, OpAdd, true, false><<<cpb, kThreads, 0, stream>>>(
+            a, b, out, partials, counters, size, size, chunk_elems, cpb);
+    DJB_POST_LAUNCH();
+}
+
+void reduce_dot(cudaStream_t stream, int vt, const void *a, const void *b, uint32_t size, void *out) {
+    const uint32_t tsize = type_size(vt);
+    if (vt != DRJIT_B200_VT_FLOAT16 && vt != DRJIT_B200_VT_FLOAT32 && vt != DRJIT_B200_VT_FLOAT64)
+        raise(DRJIT_B200_EUNSUPPORTED, "jit_reduce_dot(): no existing kernel for type=%s!", type_name(vt));
+    if (size == 0) { // empty sum
+        DJB_CUDA_CHECK(cudaMemsetAsync(out, 0, tsize, stream));
+        return;
+    }
+    switch (vt) {
+        case DRJIT_B200_VT_FLOAT16: launch_reduce_dot<__half>(stream, a, b, size, out); break;
+        case DRJIT_B200_VT_FLOAT32: launch_reduce_dot<float>(stream, a, b, size, out); break;
+        default: launch_reduce_dot<double>(stream, a, b, size, out); break;
+    }
+}
+
+} // namespace djb

@@ -1,0 +1,230 @@
+/*
+ * compress.cu -- mask compaction: indices of the non-zero bytes of a mask, ascending.
+ *
+ * Replaces CUDAThreadState::compress (ext/drjit-core/src/cuda_ts.cpp:683-763) and the kernels
+ * compress_small / compress_large / compress_large_init (resources/compress.cuh:23-156).
+ *
+ * Design. Same single-pass skeleton as prefix_reduce.cu (ticketed persistent tiles, decoupled
+ * look-back on packed 64-bit descriptors), specialised for 1-byte flags:
+ *  - a tile is 8192 mask bytes; each thread loads 2 x 16 bytes (LDG.128, warp-striped) and
+ *    turns each 16-byte unit into a 16-bit mask with three integer ops per word, so ranks come
+ *    from popc instead of a 17-step scalar scan per thread (compress.cuh:101-109);
+ *  - selected indices are first compacted into a (bank-skewed) shared-memory staging buffer
+ *    and then streamed out with fully coalesced stores; the reference issues scattered 4-byte
+ *    stores straight to global memory (compress.cuh:151-154);
+ *  - the mask is never written (the reference zero-pads the caller's buffer, cuda_ts.cpp:746-748);
+ *    the ragged tail is bounds-checked instead;
+ *  - the count goes to a device-mapped pinned word, one launch + one memset in total.
+ */
+#include "common.cuh"
+#include "runtime.h"
+
+namespace djb {
+
+constexpr uint32_t kCompThreads = 256;
+constexpr uint32_t kCompWarps = kCompThreads / 32;
+constexpr uint32_t kCompRows = 2;
+constexpr uint32_t kCompUnit = 16;                                   // mask bytes per load
+constexpr uint32_t kCompTile = kCompThreads * kCompRows * kCompUnit; // 8192
+
+enum : uint32_t { kCInvalid = 0, kCAggregate = 1, kCPrefix = 2 };
+
+struct CompressParams {
+    const uint8_t *in;
+    uint32_t *out;
+    uint64_t *state;      // tile descriptors {count << 32 | status}
+    uint32_t *ticket;
+    uint32_t *count_out;  // device-accessible
+    uint32_t size, tiles, index_base;
+    uint8_t vec;
+};
+
+/// One bit per non-zero byte of a 32-bit word (bit k <- byte k)
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w) {
+    const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; // bit 7 of each non-zero byte
+    return (((nz >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+
+/// Staging slot -> shared-memory word; one padding word per 32 keeps runs of consecutive
+/// slots written by different lanes on different banks ("compress")
+__device__ __forceinline__ uint32_t skew(uint32_t slot) { return slot + (slot >> 5); }
+
+__global__ void __launch_bounds__(kCompThreads)
+compress_kernel(const CompressParams p) {
+    __shared__ uint32_t staged[kCompTile + kCompTile / 32];
+    __shared__ uint32_t warp_cnt[kCompWarps];
+    __shared__ uint32_t tile_smem, base_smem;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t size = p.size;
+
+    while (true) {
+        if (tid == 0)
+            tile_smem = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = tile_smem;
+        if (tile >= p.tiles)
+            break;
+        const uint64_t tile_base = (uint64_t) tile * kCompTile;
+
+        // ---- load, byte flags -> bit masks ------------------------------------------
+        uint32_t mask[kCompRows], cnt[kCompRows];
+        #pragma unroll
+        for (uint32_t k = 0; k < kCompRows; ++k) {
+            const uint64_t s0 = tile_base + (uint64_t) (((warp * kCompRows + k) * 32 + lane) * kCompUnit);
+            uint32_t m = 0;
+            if (s0 < size) {
+                if (p.vec && s0 + kCompUnit <= size) {
+                    const Vec16<uint32_t> v = ld_stream<uint32_t>(p.in + s0);
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j)
+                        m |= nonzero_nibble(v.v[j]) << (4 * j);
+                } else {
+                    #pragma unroll
+                    for (uint32_t e = 0; e < kCompUnit; ++e)
+                        if (s0 + e < size && p.in[s0 + e] != 0)
+                            m |= 1u << e;
+                }
+            }
+            mask[k] = m;
+            cnt[k] = __popc(m);
+        }
+
+        // ---- ranks inside the warp -----------------------------------------------------
+        uint32_t rank[kCompRows], wtotal = 0;
+        #pragma unroll
+        for (uint32_t k = 0; k < kCompRows; ++k) {
+            uint32_t v = cnt[k];
+            #pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const uint32_t t = shfl_up(v, d);
+                if (lane >= d) v += t;
+            }
+            rank[k] = wtotal + v - cnt[k];
+            wtotal += shfl_idx(v, 31);
+        }
+        if (lane == 0)
+            warp_cnt[warp] = wtotal;
+        __syncthreads();
+
+        uint32_t wprefix = 0, ttotal = 0;
+        #pragma unroll
+        for (uint32_t w = 0; w < kCompWarps; ++w) {
+            if (w == warp) wprefix = ttotal;
+            ttotal += warp_cnt[w];
+        }
+
+        // ---- look-back for the tile's first output slot (warp 0) -----------------------
+        if (warp == 0) {
+            uint32_t excl = 0;
+            if (tile == 0) {
+                if (lane == 0)
+                    st_relaxed_u64(p.state, ((uint64_t) ttotal << 32) | kCPrefix);
+            } else {
+                if (lane == 0)
+                    st_relaxed_u64(p.state + tile, ((uint64_t) ttotal << 32) | kCAggregate);
+                int32_t pred = (int32_t) tile - 1 - (int32_t) lane;
+                while (true) {
+                    uint32_t status, value;
+                    while (true) {
+                        status = kCPrefix;
+                        value = 0;
+                        if (pred >= 0) {
+                            const uint64_t w = ld_relaxed_u64(p.state + pred);
+                            status = (uint32_t) w;
+                            value = (uint32_t) (w >> 32);
+                        }
+                        if (!__any_sync(kFullMask, status == kCInvalid))
+                            break;
+                        __nanosleep(20);
+                    }
+                    const uint32_t done = __ballot_sync(kFullMask, status == kCPrefix);
+                    const uint32_t stop = done ? (uint32_t) __ffs(done) - 1 : 31u;
+                    excl += __reduce_add_sync(kFullMask, lane <= stop ? value : 0u);
+                    if (done)
+                        break;
+                    pred -= 32;
+                }
+                if (lane == 0)
+                    st_relaxed_u64(p.state + tile, ((uint64_t) (excl + ttotal) << 32) | kCPrefix);
+            }
+            if (lane == 0) {
+                base_smem = excl;
+                if (tile == p.tiles - 1)
+                    *p.count_out = excl + ttotal;
+            }
+        }
+
+        // ---- compact the selected indices into shared memory ----------------------------
+        #pragma unroll
+        for (uint32_t k = 0; k < kCompRows; ++k) {
+            const uint32_t s0 = (uint32_t) tile_base + ((warp * kCompRows + k) * 32 + lane) * kCompUnit;
+            uint32_t m = mask[k], r = wprefix + rank[k];
+            const uint32_t idx0 = p.index_base + s0;
+            while (m) {
+                const uint32_t b = (uint32_t) __ffs(m) - 1;
+                m &= m - 1;
+                staged[skew(r)] = idx0 + b;
+                ++r;
+            }
+        }
+        __syncthreads();
+
+        // ---- coalesced write-out -------------------------------------------------------------
+        uint32_t *dst = p.out + base_smem;
+        for (uint32_t s = tid; s < ttotal; s += kCompThreads)
+            dst[s] = staged[skew(s)];
+    }
+}
+
+uint32_t compress(cudaStream_t stream, const uint8_t *in, uint32_t size, uint32_t index_base,
+                  uint32_t *out, uint32_t *count_dev, bool sync) {
+    Scratch scratch(stream);
+    uint32_t *pinned = scratch.pinned_words();
+
+    if (size == 0) { // cuda_ts.cpp:685-686
+        if (count_dev)
+            DJB_CUDA_CHECK(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), stream));
+        return 0;
+    }
+
+    const DeviceProps &dev = device_props();
+    static int occupancy = 0;
+    if (occupancy == 0) {
+        DJB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, compress_kernel,
+                                                                     kCompThreads, 0));
+        if (occupancy < 1) occupancy = 1;
+    }
+
+    CompressParams p{};
+    p.in = in; p.out = out; p.size = size; p.index_base = index_base;
+    p.tiles = ceil_div(size, kCompTile);
+    p.vec = ((uintptr_t) in % 16) == 0;
+
+    const size_t state_bytes = (size_t) p.tiles * 8;
+    uint8_t *mem = (uint8_t *) scratch.device(256 + state_bytes);
+    p.ticket = (uint32_t *) mem;
+    p.state = (uint64_t *) (mem + 256);
+    DJB_CUDA_CHECK(cudaMemsetAsync(mem, 0, 256 + state_bytes, stream));
+
+    if (count_dev) {
+        p.count_out = count_dev;
+    } else {
+        DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &p.count_out, pinned, 0));
+    }
+
+    const uint32_t grid = std::min(p.tiles, dev.sm_count * (uint32_t) occupancy);
+    compress_kernel<<<grid, kCompThreads, 0, stream>>>(p);
+    DJB_POST_LAUNCH();
+
+    if (!sync)
+        return 0;
+    // The reference synchronises here as well (jitc_sync_thread, cuda_ts.cpp:759)
+    if (count_dev) {
+        DJB_CUDA_CHECK(cudaMemcpyAsync(pinned, count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
+    DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return pinned[0];
+}
+
+} // namespace djb

@@ -1,0 +1,108 @@
+"""One-process-per-GPU sharding of the primitive path.
+
+The reference is single-device (no collectives anywhere in the tree). Here every primitive
+runs shard-locally on a contiguous index range [lo, hi) of the global array and the shards
+are combined with ONE tiny collective each -- an all-gather of per-rank scalars / counts, an
+all-reduce of a 16 KB histogram or of the 4 MB bin array. torch.distributed (NCCL on GPUs,
+gloo in the CPU tests) is only the plumbing; the combine arithmetic itself (the scan of the
+gathered totals, the final reduction of the gathered partials) reuses the same kernels.
+
+``Sharded(local=...)`` takes the object that supplies the shard-local primitives. The default
+is ``drjit_b200.ops`` (CUDA, no fallback); the CPU tests inject an oracle-backed stand-in to
+exercise the host-side logic under gloo with world_size 2.
+"""
+import torch
+import torch.distributed as dist
+
+from .ops import ReduceOp
+
+
+def shard_bounds(n, world, align=1):
+    """Contiguous, `align`-aligned shard boundaries: list of world+1 offsets covering [0, n)."""
+    per = -(-n // world)                       # ceil
+    per = -(-per // align) * align
+    return [min(r * per, n) for r in range(world + 1)]
+
+
+class Sharded:
+    def __init__(self, rank=0, world=1, group=None, local=None):
+        if local is None:
+            from . import ops as local          # CUDA path; import fails loudly without the library
+        self.rank, self.world, self.group, self.local = rank, world, group, local
+
+    # ------------------------------------------------------------------ helpers
+    def shard_range(self, n, align=1):
+        b = shard_bounds(n, self.world, align)
+        return b[self.rank], b[self.rank + 1]
+
+    def _all_gather(self, t):
+        """[W * len(t)] tensor holding every rank's `t` in rank order (device-side, no host sync)."""
+        if self.world == 1:
+            return t
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    # ------------------------------------------------------------------ reductions
+    def reduce(self, op, x, vt=None):
+        """dr.sum/prod/min/max over the global array: local reduce -> all-gather of W partials ->
+        the same kernel folds them (type- and op-exact for unsigned types, which NCCL lacks)."""
+        part = self.local.block_reduce(op, x, x.numel(), vt=vt)
+        if self.world == 1:
+            return part
+        allp = self._all_gather(part)
+        return self.local.block_reduce(op, allp, allp.numel(), vt=vt)
+
+    def dot(self, a, b):
+        part = self.local.dot(a, b)
+        if self.world == 1:
+            return part
+        allp = self._all_gather(part)
+        return self.local.block_reduce(ReduceOp.Add, allp, allp.numel())
+
+    # ------------------------------------------------------------------ prefix sum
+    def prefix_reduce(self, op, x, exclusive=True, vt=None, out=None):
+        """Global prefix reduction. Rank r needs op-reduction of all lower shards as its carry:
+        local total (one read pass) -> all-gather -> exclusive scan of the W totals (same
+        kernel) -> shard scan seeded with carry[r]. Data is read twice and written once; the
+        only inter-GPU traffic is W scalars."""
+        if self.world == 1:
+            return self.local.block_prefix_reduce(op, x, x.numel(), exclusive, False, vt=vt, out=out)
+        total = self.local.block_reduce(op, x, x.numel(), vt=vt)
+        totals = self._all_gather(total)
+        carries = self.local.block_prefix_reduce(op, totals, totals.numel(), True, False, vt=vt)
+        return self.local.prefix_reduce_carry(op, x, exclusive, False, carry_in=carries[self.rank:self.rank + 1],
+                                              vt=vt, out=out)
+
+    def prefix_sum(self, x, exclusive=True, vt=None, out=None):
+        return self.prefix_reduce(ReduceOp.Add, x, exclusive, vt, out)
+
+    # ------------------------------------------------------------------ compress
+    def compress(self, mask, index_base, out=None):
+        """Shard-local compaction with global indices. Returns (out, counts): rank r owns
+        out[:counts[r]]; the global list is the rank-order concatenation. Like the reference
+        (cuda_ts.cpp:759) the call ends with one host synchronisation to read the counts."""
+        out, count = self.local.compress_async(mask, index_base, out=out)
+        counts = self._all_gather(count)
+        return out, [int(c) & 0xFFFFFFFF for c in counts.cpu().tolist()]
+
+    # ------------------------------------------------------------------ mkperm
+    def mkperm(self, keys, bucket_count, index_base, perm=None):
+        """Shard-local permutation (entries are global indices) + global bucket histogram.
+        Returns (perm, local_hist, global_hist_host): bucket b of the global, rank-major
+        stable order is the concatenation over ranks of perm[start_r[b] : start_r[b] + local_hist[b]]."""
+        perm, hist = self.local.mkperm_sharded(keys, bucket_count, index_base, perm=perm)
+        ghist = hist
+        if self.world > 1:
+            ghist = hist.clone()
+            dist.all_reduce(ghist, op=dist.ReduceOp.SUM, group=self.group)
+        # the vcall dispatcher needs the table of non-empty buckets on the host (call.cpp:1346-1378)
+        return perm, hist, ghist.cpu()
+
+    # ------------------------------------------------------------------ scatter-add
+    def scatter_add(self, bins, value, index):
+        """Each rank accumulates its shard into its own bin array; bins are all-reduced."""
+        self.local.scatter_reduce(ReduceOp.Add, bins, value, index)
+        if self.world > 1:
+            dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=self.group)
+        return bins

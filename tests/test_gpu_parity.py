@@ -1,0 +1,527 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Integer / index results: bit-exact. Floating point: relative tolerance 1e-6 * log2(N) for f32
+(north_star), 2e-3-scale for f16, 1e-13-scale for f64, stated next to each check.
+The grids follow the reference's own tests (ext/drjit-core/tests/reductions.cpp,
+tests/test_reduction.py, tests/test_memop.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import drjit_b200 as dr
+from drjit_b200 import ReduceMode, ReduceOp, VarType
+from oracle import capi
+from tests.gpu_util import NP, OPS, VT, to_dev, to_np
+from tests.golden import loader
+from tests.golden.make_golden import digest, make_input
+
+pytestmark = pytest.mark.gpu
+
+# ext/drjit-core/tests/reductions.cpp:73-76
+RED_SIZES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 32, 60, 128, 250, 333, 1024, 16384,
+             16388 * 10, 9973 * 17, 98973 * 17 * 3]
+INT_TYPES = ["u8", "i32", "u32", "i64", "u64"]
+FLT_TYPES = ["f16", "f32", "f64"]
+
+
+def ftol(vt, n):
+    base = {"f16": 1.5e-3, "f32": 1e-6, "f64": 1e-14}[vt]
+    return base * max(1.0, np.log2(max(n, 2)))
+
+
+def assert_close(got, exp, vt, n, what):
+    got = got.astype(np.float64); exp = exp.astype(np.float64)
+    scale = np.maximum(np.abs(exp), 1.0)
+    err = np.abs(got - exp) / scale
+    assert np.all(err <= ftol(vt, n)), f"{what}: max rel err {err.max():.3e} > {ftol(vt, n):.3e}"
+
+
+# --------------------------------------------------------------------------- block_reduce
+@pytest.mark.parametrize("vt", ["u32", "u64"])
+def test_block_sum_reference_grid(vt):
+    """reductions.cpp:122-151: every (size, block_size) pair of red_sizes, exact"""
+    for size in RED_SIZES:
+        x = capi.fmix32(size) if vt == "u32" else capi.fmix32_u64(size)
+        xd = to_dev(x, vt)
+        for bs in RED_SIZES:
+            if bs > size:
+                continue
+            got = to_np(dr.block_reduce(ReduceOp.Add, xd, bs, vt=VT[vt]), vt)
+            assert np.array_equal(got, capi.block_reduce(vt, "add", x, bs)), (size, bs)
+
+
+@pytest.mark.parametrize("vt", INT_TYPES)
+@pytest.mark.parametrize("op", ["add", "mul", "min", "max", "and", "or"])
+def test_block_reduce_int_ops(vt, op):
+    for size in [1, 7, 333, 16384 + 4, 9973 * 17]:
+        x = make_input(vt, size)
+        for misalign in (0, 1):
+            xd = to_dev(x, vt, misalign)
+            for bs in [1, 2, 3, 7, 32, 250, 256, 1024, 5000, 65536, size]:
+                if bs > size:
+                    continue
+                got = to_np(dr.block_reduce(OPS[op], xd, bs, vt=VT[vt]), vt)
+                assert np.array_equal(got, capi.block_reduce(vt, op, x, bs)), (size, bs, misalign)
+
+
+@pytest.mark.parametrize("vt", FLT_TYPES)
+@pytest.mark.parametrize("op", ["add", "mul", "min", "max"])
+def test_block_reduce_float_ops(vt, op):
+    for size in [1, 7, 333, 16384 + 4, 9973 * 17]:
+        x = make_input(vt, size)
+        if op == "mul":
+            x = (1.0 + (x.astype(np.float64) - 0.5) * 1e-3).astype(NP[vt])  # keep products finite
+        xd = to_dev(x, vt)
+        for bs in [2, 3, 32, 250, 256, 1024, 5000, size]:
+            if bs > size:
+                continue
+            got = to_np(dr.block_reduce(OPS[op], xd, bs, vt=VT[vt]), vt)
+            exp = capi.block_reduce(vt, op, x, bs, acc64=True)
+            if op in ("min", "max"):
+                assert np.array_equal(got, exp), (size, bs)
+            else:
+                assert_close(got, exp, vt, bs, f"{vt} {op} size={size} bs={bs}")
+
+
+def test_block_reduce_golden_fixture():
+    """against outputs of the unmodified reference (tests/golden/ref_llvm.npz), integer digests"""
+    digests, _ = loader.load()
+    for vt in ["u8", "i32", "u32", "i64", "u64"]:
+        for n in [333, 5000, 16384 + 4]:
+            x = make_input(vt, n); xd = to_dev(x, vt)
+            for bs in [2, 7, 60, 250, 1024]:
+                for op in ["add", "mul", "min", "max", "and", "or"]:
+                    got = to_np(dr.block_reduce(OPS[op], xd, bs, vt=VT[vt]), vt)
+                    assert digest(got)[0] == digests[f"br/{vt}/{op}/{n}/{bs}"], (vt, n, bs, op)
+                    for ex in (0, 1):
+                        for rev in (0, 1):
+                            got = to_np(dr.block_prefix_reduce(OPS[op], xd, bs, ex, rev, vt=VT[vt]), vt)
+                            assert digest(got)[0] == digests[f"bp/{vt}/{op}/{n}/{bs}/{ex}{rev}"], (vt, n, bs, op, ex, rev)
+
+
+def test_block_reduce_errors_and_edges():
+    """cuda_ts.cpp:200-213: empty no-op, invalid block size raises, block_size == 1 copies"""
+    x = to_dev(capi.fmix32(10), "u32")
+    assert dr.block_reduce(ReduceOp.Add, x[:0], 1).numel() == 0
+    for bs in (0, 11):
+        with pytest.raises(RuntimeError, match="invalid block size"):
+            dr.block_reduce(ReduceOp.Add, x, bs, vt=VarType.UInt32)
+        with pytest.raises(RuntimeError, match="invalid block size"):
+            dr.block_prefix_reduce(ReduceOp.Add, x, bs, vt=VarType.UInt32)
+    assert torch.equal(dr.block_reduce(ReduceOp.Max, x, 1, vt=VarType.UInt32), x)
+    f = torch.ones(8, device="cuda")
+    with pytest.raises(RuntimeError, match="no existing kernel"):
+        dr.block_reduce(ReduceOp.And, f, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dr.sum(torch.ones(4))
+
+
+def test_full_reduction_large():
+    """dr.sum at 2^28 f32 (BASELINE config 1): tolerance 1e-6*log2(N); u32: exact"""
+    n = 1 << 28
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    dr.ops.fill_fmix32(x, 1)
+    got = float(dr.sum(x).item())
+    exp = float(capi.block_reduce("f32", "add", capi.unit_f32(n), n, acc64=True)[0])
+    assert abs(got - exp) <= 1e-6 * 28 * abs(exp), (got, exp)
+    # block_reduce(Add, 256): every block against float64 torch reduction
+    out = dr.block_reduce(ReduceOp.Add, x, 256)
+    ref = x.view(-1, 256).to(torch.float64).sum(dim=1)
+    assert torch.all((out.to(torch.float64) - ref).abs() <= 1e-6 * 8 * ref.abs().clamp_min(1.0))
+    # u32, exact (wraps mod 2^32)
+    xi = torch.empty(n, dtype=torch.int32, device="cuda")
+    dr.ops.fill_fmix32(xi, 0)
+    got = int(dr.sum(xi, vt=VarType.UInt32).item()) & 0xFFFFFFFF
+    assert got == int(capi.fmix32(n).sum(dtype=np.uint32))
+    assert (int(dr.min(xi, vt=VarType.UInt32).item()) & 0xFFFFFFFF) == int(capi.fmix32(n).min())
+    assert (int(dr.max(xi, vt=VarType.Int32).item())) == int(capi.fmix32(n).view(np.int32).max())
+
+
+def test_all_any():
+    """reductions.cpp:78-107: single-bit flips over sizes 23 i^3 + 1"""
+    rng = np.random.default_rng(1)
+    for i in list(range(0, 100, 9)) + [99]:
+        size = 23 * i ** 3 + 1
+        f = torch.zeros(size, dtype=torch.bool, device="cuda")
+        t = torch.ones(size, dtype=torch.bool, device="cuda")
+        assert dr.all(t) and dr.any(t) and not dr.all(f) and not dr.any(f)
+        for _ in range(4):
+            k = int(rng.integers(0, size))
+            f[k] = True; t[k] = False
+            if size == 1:
+                assert not dr.all(t) and not dr.any(t) and dr.all(f) and dr.any(f)
+            else:
+                assert not dr.all(t) and dr.any(t) and not dr.all(f) and dr.any(f)
+            f[k] = False; t[k] = True
+    # misaligned mask (sub-range of an allocation)
+    t = torch.ones(1000, dtype=torch.bool, device="cuda")[3:]
+    assert dr.all(t)
+    t[500] = False
+    assert not dr.all(t) and dr.any(t)
+
+
+@pytest.mark.parametrize("vt", FLT_TYPES)
+def test_dot(vt):
+    for n in [1, 5, 100, 5000, 1 << 20, (1 << 22) + 3]:
+        a = make_input(vt, n); b = make_input(vt, n)[::-1].copy()
+        for misalign in (0, 1):
+            got = to_np(dr.dot(to_dev(a, vt, misalign), to_dev(b, vt, misalign)), vt)[0]
+            exp = capi.reduce_dot(vt, a, b, acc64=True)
+            tol = ftol(vt, n) * max(1.0, abs(float(exp)))
+            if vt == "f16":
+                tol = max(tol, 2e-3 * abs(float(exp)))
+            assert abs(float(got) - float(exp)) <= tol, (vt, n, got, exp)
+    got = to_np(dr.dot(to_dev(make_input("f32", 1001), "f32"), to_dev(make_input("f32", 1001), "f32", 1)), "f32")
+    assert abs(float(got[0]) - float(capi.reduce_dot("f32", make_input("f32", 1001), make_input("f32", 1001), acc64=True))) < 1e-3
+
+
+# --------------------------------------------------------------------------- prefix reductions
+@pytest.mark.parametrize("vt", ["u32", "u64"])
+@pytest.mark.parametrize("exclusive", [0, 1])
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_block_prefix_sum_reference_grid(vt, exclusive, reverse):
+    """reductions.cpp:153-267: all four variants over the red_sizes grid, exact"""
+    sizes = [s for s in RED_SIZES if s <= 9973 * 17]
+    for size in sizes:
+        x = capi.fmix32(size) if vt == "u32" else capi.fmix32_u64(size)
+        xd = to_dev(x, vt)
+        for bs in sizes:
+            if bs > size:
+                continue
+            got = to_np(dr.block_prefix_reduce(ReduceOp.Add, xd, bs, exclusive, reverse, vt=VT[vt]), vt)
+            assert np.array_equal(got, capi.block_prefix_reduce(vt, "add", x, bs, exclusive, reverse)), (size, bs)
+
+
+def test_prefix_sum_largest_reference_size_and_inplace():
+    n = RED_SIZES[-1]
+    x = capi.fmix32(n)
+    for misalign in (0, 1):
+        xd = to_dev(x, "u32", misalign)
+        for ex in (0, 1):
+            for rev in (0, 1):
+                for bs in (n, 16388 * 10, 1000):
+                    got = to_np(dr.block_prefix_reduce(ReduceOp.Add, xd, bs, ex, rev, vt=VarType.UInt32), "u32")
+                    assert np.array_equal(got, capi.block_prefix_reduce("u32", "add", x, bs, ex, rev)), (misalign, ex, rev, bs)
+    # in place (jit.h:2346-2364)
+    xd = to_dev(x, "u32")
+    dr.block_prefix_reduce(ReduceOp.Add, xd, n, True, False, vt=VarType.UInt32, out=xd)
+    assert np.array_equal(to_np(xd, "u32"), capi.block_prefix_reduce("u32", "add", x, n, 1, 0))
+
+
+@pytest.mark.parametrize("vt", INT_TYPES)
+@pytest.mark.parametrize("op", ["add", "mul", "min", "max", "and", "or"])
+def test_block_prefix_reduce_int_ops(vt, op):
+    for size in [1, 333, 40000 + 3]:
+        x = make_input(vt, size); xd = to_dev(x, vt)
+        for bs in [1, 2, 3, 7, 250, 256, 4096, 10000, size]:
+            if bs > size:
+                continue
+            for ex, rev in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                got = to_np(dr.block_prefix_reduce(OPS[op], xd, bs, ex, rev, vt=VT[vt]), vt)
+                assert np.array_equal(got, capi.block_prefix_reduce(vt, op, x, bs, ex, rev)), (size, bs, ex, rev)
+
+
+@pytest.mark.parametrize("vt", FLT_TYPES)
+@pytest.mark.parametrize("op", ["add", "min", "max"])
+def test_block_prefix_reduce_float_ops(vt, op):
+    for size in [333, 40000 + 3]:
+        x = make_input(vt, size); xd = to_dev(x, vt)
+        for bs in [2, 7, 256, 5000, size]:
+            if bs > size:
+                continue
+            for ex, rev in ((0, 0), (1, 1)):
+                got = to_np(dr.block_prefix_reduce(OPS[op], xd, bs, ex, rev, vt=VT[vt]), vt)
+                exp = capi.block_prefix_reduce(vt, op, x, bs, ex, rev, acc64=True)
+                if op == "add":
+                    assert_close(got, exp, vt, bs, f"{vt} prefix size={size} bs={bs}")
+                else:
+                    assert np.array_equal(got, exp), (size, bs, ex, rev)
+
+
+def test_prefix_literals():
+    """tests/test_memop.py:734-756, tests/test_reduction.py:370-387"""
+    x = torch.tensor([1, 2, 3, 4, 5, 6], dtype=torch.float32, device="cuda")
+    exp_sum = {1: [1, 2, 3, 4, 5, 6], 2: [3, 7, 11], 3: [6, 15], 4: [10, 11], 5: [15, 6], 6: [21]}
+    exp_psum = {1: [0] * 6, 2: [0, 1, 0, 3, 0, 5], 3: [0, 1, 3, 0, 4, 9], 4: [0, 1, 3, 6, 0, 5],
+                5: [0, 1, 3, 6, 10, 0], 6: [0, 1, 3, 6, 10, 15]}
+    for dtype in (torch.float32, torch.float64, torch.int32, torch.int64, torch.float16):
+        xx = x.to(dtype)
+        for bs in range(1, 7):
+            assert dr.block_sum(xx, bs).tolist() == exp_sum[bs]
+            assert dr.block_prefix_sum(xx, bs).tolist() == exp_psum[bs]
+    assert dr.prefix_sum(x[:3]).tolist() == [0, 1, 3]
+    assert dr.cumsum(x[:3]).tolist() == [1, 3, 6]
+
+
+def test_prefix_sum_2_30_properties():
+    """exclusive u32 prefix sum at the BASELINE size 2^30 through size-independent properties:
+    out[0] == 0, out[i+1] - out[i] == in[i] (mod 2^32), out[n-1] + in[n-1] == sum"""
+    n = 1 << 30
+    x = torch.empty(n, dtype=torch.int32, device="cuda")
+    dr.ops.fill_fmix32(x, 0)
+    out = dr.prefix_sum(x, vt=VarType.UInt32)
+    assert int(out[0].item()) == 0
+    assert bool(torch.all(out[1:] - out[:-1] == x[:-1]))
+    total = dr.sum(x, vt=VarType.UInt32)
+    assert int((out[-1] + x[-1]).item()) == int(total.item())
+    del out
+    # first 2^22 entries bit-exact against the oracle
+    exp = capi.block_prefix_reduce("u32", "add", capi.fmix32(1 << 22), 1 << 22, 1, 0)
+    out = dr.prefix_sum(x[:1 << 22], vt=VarType.UInt32)
+    assert np.array_equal(to_np(out, "u32"), exp)
+
+
+# --------------------------------------------------------------------------- compress
+def test_compress_reference_grid():
+    """reductions.cpp:269-313: sizes 23 i^3 + 1, n_ones 23 j^3 + 1 random ones, exact list + count"""
+    rng = np.random.default_rng(0)
+    for i in range(0, 30, 2):
+        size = 23 * i ** 3 + 1
+        for j in range(0, i + 1, 3):
+            data = np.zeros(size, np.uint8)
+            data[rng.integers(0, size, 23 * j ** 3 + 1)] = 1
+            got = to_np(dr.compress(to_dev(data, "u8")), "u32")
+            assert np.array_equal(got, np.flatnonzero(data).astype(np.uint32)), (size, j)
+
+
+@pytest.mark.parametrize("size", [1, 4095, 4096, 4097, 8192, 100000, 200001])
+@pytest.mark.parametrize("density", [0.0, 0.01, 0.5, 0.99, 1.0])
+def test_compress_large(size, density):
+    """tests/test_reduction.py:401-415 (same seeds), bool masks, misaligned variant too"""
+    rng = np.random.default_rng(seed=0xC0FFEE ^ size)
+    mask = rng.uniform(0.0, 1.0, size) < density
+    exp = np.flatnonzero(mask).astype(np.uint32)
+    m = torch.from_numpy(mask).cuda()
+    assert np.array_equal(to_np(dr.compress(m), "u32"), exp)
+    buf = torch.zeros(size + 5, dtype=torch.bool, device="cuda")
+    buf[5:] = m
+    assert np.array_equal(to_np(dr.compress(buf[5:]), "u32"), exp)
+    # the mask must not be modified (the reference zero-pads it, we do not)
+    assert torch.equal(buf[5:], m)
+
+
+def test_compress_literals_and_golden():
+    a = torch.tensor([0, 1, 1, 0, 0, 1, 0, 1, 1], dtype=torch.bool, device="cuda")
+    assert dr.compress(a).tolist() == [1, 2, 5, 7, 8]
+    assert dr.compress(torch.zeros(3, dtype=torch.bool, device="cuda")).tolist() == []
+    assert dr.compress(torch.zeros(0, dtype=torch.bool, device="cuda")).tolist() == []
+    digests, _ = loader.load()
+    for n in [1, 9, 4095, 4096, 4097, 8192, 20001]:
+        for thr in [0, 3, 128, 253, 256]:
+            got = to_np(dr.compress(to_dev(capi.mask_u8(n, thr), "u8")), "u32")
+            assert digest(got)[0] == digests[f"compress/{n}/{thr}"]
+
+
+def test_compress_2_30_properties():
+    """BASELINE size 2^30, density 50 %: count == popcount, strictly increasing, mask[out] all set,
+    first 2^22 indices bit-exact against the oracle"""
+    n = 1 << 30
+    m = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dr.ops.fill_fmix32(m, 2, and_=128)
+    out = dr.compress(m)
+    count = out.numel()
+    assert count == int(m.sum(dtype=torch.int64).item())
+    o = out.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert bool(torch.all(o[1:] > o[:-1]))
+    assert bool(torch.all(m[o] == 1))
+    exp = capi.compress(capi.mask_u8(1 << 22, 128))
+    assert np.array_equal(o[:exp.size].cpu().numpy().astype(np.uint32), exp)
+
+
+# --------------------------------------------------------------------------- mkperm
+def check_mkperm(keys, buckets, perm, table, block_size=None):
+    """The reference's own acceptance test (reductions.cpp:360-398): ids / starts / sizes of
+    the non-empty buckets and the *sorted* contents of every bucket."""
+    n = keys.size
+    bs = block_size or n
+    exp_perm, exp_off, exp_unique = capi.block_mkperm(keys, bs, buckets)
+    if table is not None:
+        t = table.numpy().astype(np.uint32)
+        assert t.shape[0] == exp_unique
+        assert np.array_equal(t.reshape(-1), exp_off[:4 * exp_unique])
+    # per bucket (and per group) the contents must agree as sets; sorting each run of equal
+    # keys makes an unstable-but-valid permutation comparable with the stable oracle
+    got = perm.astype(np.int64)
+    assert np.array_equal(np.sort(got), np.arange(n)), "not a permutation"
+    group = np.arange(n) // bs
+    key_of = keys[got].astype(np.int64)
+    assert np.array_equal(group[got], group), "element left its sorting group"
+    order_key = group * (buckets + 1) + key_of
+    assert np.all(np.diff(order_key) >= 0), "keys not sorted inside groups"
+    canon = np.lexsort((got, order_key))
+    assert np.array_equal(got[canon], exp_perm.astype(np.int64))
+
+
+def test_mkperm_reference_grid():
+    """reductions.cpp:315-406 (sizes / bucket counts 23 i^3 + 1)"""
+    rng = np.random.default_rng(0)
+    for i in range(0, 30, 3):
+        size = 23 * i ** 3 + 1
+        for j in range(0, i + 1, 3):
+            buckets = 23 * j ** 3 + 1
+            keys = rng.integers(0, buckets, size).astype(np.uint32)
+            perm, table = dr.block_mkperm(to_dev(keys, "u32"), size, buckets)
+            torch.cuda.synchronize()
+            check_mkperm(keys, buckets, to_np(perm, "u32"), table)
+
+
+def test_mkperm_stable_variant_is_bit_exact():
+    """bucket counts that fit the per-warp variant must reproduce the reference's CPU
+    (stable) permutation bit for bit, including the golden digests"""
+    digests, _ = loader.load()
+    for n, buckets in [(1, 1), (24, 1), (185, 24), (622, 185), (1473, 622), (20001, 4096), (20001, 37)]:
+        keys = capi.fmix32(n) % np.uint32(buckets)
+        perm, table = dr.block_mkperm(to_dev(keys, "u32"), n, buckets)
+        torch.cuda.synchronize()
+        assert digest(to_np(perm, "u32"))[0] == digests[f"mkperm/{n}/{buckets}/perm"], (n, buckets)
+        assert digest(table.numpy().astype(np.uint32).reshape(-1))[0] == digests[f"mkperm/{n}/{buckets}/offsets"]
+        for bs in (7, 256):
+            if bs < n:
+                perm, table = dr.block_mkperm(to_dev(keys, "u32"), bs, buckets)
+                torch.cuda.synchronize()
+                assert table is None
+                assert digest(to_np(perm, "u32"))[0] == digests[f"mkperm_block/{n}/{buckets}/{bs}"], (n, buckets, bs)
+
+
+@pytest.mark.parametrize("buckets", [1, 2, 37, 256, 4096, 8000, 50000, 100000])
+def test_mkperm_variants(buckets):
+    """per-warp (stable), per-CTA and global-atomic variants; single group and sorting groups"""
+    n = 1_000_003
+    keys = capi.fmix32(n) % np.uint32(buckets)
+    kd = to_dev(keys, "u32")
+    perm, table = dr.block_mkperm(kd, n, buckets)
+    torch.cuda.synchronize()
+    check_mkperm(keys, buckets, to_np(perm, "u32"), table)
+    for bs in (1000, 65536):
+        perm, table = dr.block_mkperm(kd, bs, buckets)
+        torch.cuda.synchronize()
+        check_mkperm(keys, buckets, to_np(perm, "u32"), None, block_size=bs)
+    kd1 = to_dev(keys, "u32", 1)   # misaligned keys
+    perm, table = dr.block_mkperm(kd1, n, buckets)
+    torch.cuda.synchronize()
+    check_mkperm(keys, buckets, to_np(perm, "u32"), table)
+
+
+def test_mkperm_baseline_config():
+    """BASELINE config: 2^26 keys, 4096 buckets; uniform and skewed ids"""
+    n = 1 << 26
+    for skew in (False, True):
+        keys = capi.fmix32(n, mask=4095)
+        if skew:
+            keys = np.minimum(keys, capi.fmix32(n, xor=0x9E3779B9, mask=4095))
+        perm, table = dr.block_mkperm(to_dev(keys, "u32"), n, 4096)
+        torch.cuda.synchronize()
+        check_mkperm(keys, 4096, to_np(perm, "u32"), table)
+
+
+def test_mkperm_errors():
+    k = torch.zeros(10, dtype=torch.int32, device="cuda")
+    with pytest.raises(dr._lib.FatalError, match="bucket_count cannot be zero"):
+        dr.block_mkperm(k, 10, 0)
+    perm, table = dr.block_mkperm(k[:0], 0, 5)
+    assert perm.numel() == 0
+
+
+# --------------------------------------------------------------------------- scatter_reduce
+@pytest.mark.parametrize("mode", [ReduceMode.Auto, ReduceMode.Direct, ReduceMode.Local])
+def test_scatter_reduce_modes_agree(mode):
+    """tests/test_memop.py:423-499: all modes must agree, target sizes 2^0..2^9 (+ larger)"""
+    n = 100_003
+    for k in list(range(0, 10)) + [16, 20]:
+        bins = 1 << k
+        idx = capi.fmix32(n, xor=0x85EBCA6B, mask=bins - 1)
+        for vt in ("u32", "f32", "f64", "i64"):
+            val = make_input(vt, n)
+            if vt in ("u32", "i64"):
+                val = (val.astype(np.int64) % 1000).astype(NP[vt])
+            tgt = np.zeros(bins, NP[vt])
+            exp = capi.scatter_reduce(vt, "add", tgt, val, idx, acc64=True)
+            got = to_np(dr.scatter_reduce(ReduceOp.Add, to_dev(tgt, vt), to_dev(val, vt), to_dev(idx, "u32"),
+                                          mode=mode, vt=VT[vt]), vt)
+            if vt in ("u32", "i64"):
+                assert np.array_equal(got, exp), (k, vt)
+            else:
+                assert_close(got, exp, vt, max(2, n // bins), f"scatter add {vt} bins=2^{k}")
+
+
+@pytest.mark.parametrize("op", ["min", "max", "and", "or"])
+def test_scatter_reduce_other_ops(op):
+    n, bins = 50_001, 97
+    idx = capi.fmix32(n, xor=1) % np.uint32(bins)
+    mask = (capi.fmix32(n, xor=2) & 3) != 0
+    for vt in ("u32", "i32", "u64", "i64", "f32", "f64"):
+        if op in ("and", "or") and vt in ("f32", "f64"):
+            with pytest.raises(RuntimeError, match="does not support"):
+                dr.scatter_reduce(OPS[op], torch.zeros(4, device="cuda"), torch.zeros(4, device="cuda"),
+                                  torch.zeros(4, dtype=torch.int32, device="cuda"))
+            continue
+        val = make_input(vt, n)
+        init = make_input(vt, bins)
+        exp = capi.scatter_reduce(vt, op, init, val, idx, mask=mask.astype(np.uint8))
+        for mode in (ReduceMode.Direct, ReduceMode.Local):
+            got = to_np(dr.scatter_reduce(OPS[op], to_dev(init, vt), to_dev(val, vt), to_dev(idx, "u32"),
+                                          active=torch.from_numpy(mask).cuda(), mode=mode, vt=VT[vt]), vt)
+            assert np.array_equal(got, exp), (vt, op, mode)
+
+
+def test_scatter_add_baseline_config():
+    """BASELINE config 5 (one shard): 2^25 f32 values into 2^20 bins; tolerance 1e-6*log2(count)"""
+    n, bins = 1 << 25, 1 << 20
+    val = capi.unit_f32(n)
+    idx = capi.fmix32(n, xor=0x85EBCA6B, mask=bins - 1)
+    exp = capi.scatter_reduce("f32", "add", np.zeros(bins, np.float32), val, idx, acc64=True)
+    got = to_np(dr.scatter_add(torch.zeros(bins, device="cuda"), to_dev(val, "f32"), to_dev(idx, "u32")), "f32")
+    assert_close(got, exp, "f32", 32, "histogram")
+
+
+# --------------------------------------------------------------------------- misc
+def test_memset_poke_aggregate():
+    from drjit_b200._lib import check, lib
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for isize, pattern in [(1, b"\x07"), (2, b"\x34\x12"), (4, b"\x78\x56\x34\x12"), (8, bytes(range(1, 9))),
+                           (4, b"\0\0\0\0"), (8, b"\xff" * 8)]:
+        for n in (1, 3, 1000, 100_001):
+            for mis in (0, 1):
+                buf = torch.zeros((n + mis) * isize + 16, dtype=torch.uint8, device="cuda")
+                view = buf[mis * isize:(mis + n) * isize]
+                dr.ops.memset(view, pattern)
+                exp = np.frombuffer(pattern * n, np.uint8)
+                assert np.array_equal(view.cpu().numpy(), exp), (isize, n, mis)
+                assert int(buf[(mis + n) * isize:].sum().item()) == 0 and int(buf[:mis * isize].sum().item()) == 0
+    with pytest.raises(RuntimeError, match="invalid element size"):
+        dr.ops.memset(torch.zeros(12, dtype=torch.uint8, device="cuda"), b"\1\2\3")
+    # poke
+    buf = torch.zeros(4, dtype=torch.int64, device="cuda")
+    v = ctypes.c_uint64(0x1122334455667788)
+    check(lib.drjit_b200_poke(stream, ctypes.c_void_p(buf.data_ptr() + 8), ctypes.byref(v), 8))
+    v4 = ctypes.c_uint32(0xDEADBEEF)
+    check(lib.drjit_b200_poke(stream, ctypes.c_void_p(buf.data_ptr() + 16), ctypes.byref(v4), 4))
+    assert buf.tolist() == [0, 0x1122334455667788, 0xDEADBEEF, 0]
+    # aggregate (resources/misc.cuh:41-61): literals (size > 0) and dereferenced sources (size < 0)
+    src = torch.tensor([0x0102030405060708], dtype=torch.int64, device="cuda")
+    entries = np.zeros(4, dtype=[("size", "<i2"), ("kind", "<u2"), ("offset", "<u4"), ("src", "<u8")])
+    entries[0] = (4, 0, 0, 0xAABBCCDD)
+    entries[1] = (-8, 0, 8, src.data_ptr())
+    entries[2] = (1, 0, 4, 0x7F)
+    entries[3] = (-2, 0, 6, src.data_ptr())
+    agg = torch.from_numpy(entries.view(np.uint8).copy()).cuda()
+    dst = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    check(lib.drjit_b200_aggregate(stream, ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(agg.data_ptr()), 4))
+    exp = np.zeros(16, np.uint8)
+    exp[0:4] = np.frombuffer((0xAABBCCDD).to_bytes(4, "little"), np.uint8)
+    exp[4] = 0x7F
+    exp[6:8] = [0x08, 0x07]
+    exp[8:16] = np.frombuffer((0x0102030405060708).to_bytes(8, "little"), np.uint8)
+    assert np.array_equal(dst.cpu().numpy(), exp)
+
+
+def test_launch_accounting_and_native_library_loaded():
+    """the CUDA path is the one that runs: launches are counted and the .so is mapped"""
+    dr.launch_count(reset=True)
+    x = torch.ones(1 << 20, device="cuda")
+    dr.sum(x); dr.prefix_sum(x)
+    assert dr.launch_count() >= 2
+    with open("/proc/self/maps") as f:
+        assert "libdrjit_b200.so" in f.read()
