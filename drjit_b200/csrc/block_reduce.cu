@@ -462,12 +462,11 @@ void block_reduce_bool(cudaStream_t stream, const uint8_t *values, uint32_t size
         raise(DRJIT_B200_EINVAL, "jit_block_reduce_bool(): op must be And or Or!");
     if (((uintptr_t) out % 4) != 0)
         raise(DRJIT_B200_EINVAL, "jit_block_reduce_bool(): output must be 4-byte aligned!");
-    Scratch scratch(stream);
     if (size == 0) { // reduction over nothing = identity
-        const uint32_t ident = op == DRJIT_B200_OP_AND ? 0x01010101u : 0u;
-        DJB_CUDA_CHECK(cudaMemcpyAsync(out, &ident, 4, cudaMemcpyHostToDevice, stream));
+        DJB_CUDA_CHECK(cudaMemsetAsync(out, op == DRJIT_B200_OP_AND ? 1 : 0, 4, stream));
         return;
     }
+    Scratch scratch(stream);
     launch_reduce_bool(stream, scratch, values, size, out, op);
 }
 

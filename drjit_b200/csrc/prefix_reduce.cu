@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "runtime.h"
 
+#include <cstdlib>
+
 namespace djb {
 
 constexpr uint32_t kScanThreads = 256;
@@ -93,13 +95,25 @@ struct PrefixParams {
 // ---------------------------------------------------------------------------
 //  Kernel
 // ---------------------------------------------------------------------------
-template <typename T, typename Op, bool SEG, bool VEC>
+/// Tile geometry. A "unit" is what one thread loads at once (a 128-bit vector, or one element
+/// on the unaligned path); a thread owns ROWS units. Large arrays use 4x larger tiles: at
+/// B200 bandwidth a 16 KiB tile would start ~200 tiles/us, more than a 64-descriptor
+/// look-back window can follow ("prefix_reduce").
+template <typename T, bool VEC, bool BIG> struct ScanGeom {
+    static constexpr uint32_t V = VEC ? 16 / sizeof(T) : 1;
+    static constexpr uint32_t BASE_ROWS = VEC ? (V >= 16 ? 1 : (V == 8 ? 2 : 4)) : 4;
+    static constexpr uint32_t ROWS = BASE_ROWS * (BIG ? 4 : 1);
+    static constexpr uint32_t TILE = kScanThreads * ROWS * V;
+};
+
+template <typename T, typename Op, bool SEG, bool VEC, bool BIG>
 __global__ void __launch_bounds__(kScanThreads)
 prefix_reduce_kernel(const PrefixParams p) {
     using A = acc_t<T>;
-    constexpr uint32_t V = VEC ? 16 / sizeof(T) : 1;                  // elements per unit
-    constexpr uint32_t ROWS = VEC ? (V >= 16 ? 1 : (V == 8 ? 2 : 4)) : 4; // units per thread
-    constexpr uint32_t TILE = kScanThreads * ROWS * V;
+    using Geom = ScanGeom<T, VEC, BIG>;
+    constexpr uint32_t V = Geom::V;         // elements per unit
+    constexpr uint32_t ROWS = Geom::ROWS;   // units per thread
+    constexpr uint32_t TILE = Geom::TILE;
     const A ident = Op::template identity<A>();
 
     __shared__ uint32_t tile_smem;
@@ -243,20 +257,15 @@ prefix_reduce_kernel(const PrefixParams p) {
                 else if (lane == 0)
                     state.publish(tile, kAggregate, tv);
 
+                // Each round inspects 64 predecessors (two descriptors per lane, both loads in
+                // flight together): window 0 = the nearest 32 tiles, window 1 = the 32 before.
                 int32_t pred = (int32_t) tile - 1 - (int32_t) lane;
-                while (true) {
-                    // every lane polls its own predecessor; lanes past the start of the
-                    // array behave like a finished tile holding the identity
-                    uint32_t status;
-                    A value;
-                    while (true) {
-                        status = kPrefix;
-                        value = ident;
-                        if (pred >= 0)
-                            state.load((uint32_t) pred, status, value);
-                        if (!__any_sync(kFullMask, status == kInvalid))
-                            break;
+                // folds one window of 32 descriptors into `excl`; true once a complete prefix was found
+                auto consume = [&](int32_t first, uint32_t status, A value) -> bool {
+                    while (__any_sync(kFullMask, status == kInvalid)) {
                         __nanosleep(20);
+                        if (first >= 0)
+                            state.load((uint32_t) first, status, value);
                     }
                     const uint32_t done = __ballot_sync(kFullMask, status == kPrefix);
                     // nearest predecessor holding a complete prefix (lowest lane)
@@ -264,9 +273,17 @@ prefix_reduce_kernel(const PrefixParams p) {
                     A contrib = lane <= stop ? value : ident;
                     contrib = WarpReduce<Op, A>::template run<32>(contrib);
                     excl = Op::template apply<A>(contrib, excl);
-                    if (done)
-                        break;
-                    pred -= 32;
+                    return done != 0;
+                };
+                while (true) {
+                    // lanes past the start of the array act like a finished tile holding the identity
+                    uint32_t status0 = kPrefix, status1 = kPrefix;
+                    A value0 = ident, value1 = ident;
+                    if (pred >= 0) state.load((uint32_t) pred, status0, value0);
+                    if (pred >= 32) state.load((uint32_t) (pred - 32), status1, value1);
+                    if (consume(pred, status0, value0)) break;
+                    if (consume(pred - 32, status1, value1)) break;
+                    pred -= 64;
                 }
                 if (lane == 0 && !tf)
                     state.publish(tile, kPrefix, Op::template apply<A>(excl, tv));
@@ -324,18 +341,16 @@ prefix_reduce_kernel(const PrefixParams p) {
 // ---------------------------------------------------------------------------
 //  Host side
 // ---------------------------------------------------------------------------
-template <typename T, typename Op, bool SEG, bool VEC>
-static void launch_prefix_variant(cudaStream_t stream, PrefixParams &p) {
+template <typename T, typename Op, bool SEG, bool VEC, bool BIG>
+static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     using A = acc_t<T>;
-    constexpr uint32_t V = VEC ? 16 / sizeof(T) : 1;
-    constexpr uint32_t ROWS = VEC ? (V >= 16 ? 1 : (V == 8 ? 2 : 4)) : 4;
-    constexpr uint32_t TILE = kScanThreads * ROWS * V;
+    constexpr uint32_t TILE = ScanGeom<T, VEC, BIG>::TILE;
     const DeviceProps &dev = device_props();
 
     static int occupancy = 0; // per instantiation
     if (occupancy == 0) {
         DJB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occupancy, prefix_reduce_kernel<T, Op, SEG, VEC>, kScanThreads, 0));
+            &occupancy, prefix_reduce_kernel<T, Op, SEG, VEC, BIG>, kScanThreads, 0));
         if (occupancy < 1) occupancy = 1;
     }
 
@@ -348,8 +363,27 @@ static void launch_prefix_variant(cudaStream_t stream, PrefixParams &p) {
     DJB_CUDA_CHECK(cudaMemsetAsync(mem, 0, 256 + state_bytes, stream));
 
     const uint32_t grid = std::min(p.tiles, dev.sm_count * (uint32_t) occupancy);
-    prefix_reduce_kernel<T, Op, SEG, VEC><<<grid, kScanThreads, 0, stream>>>(p);
+    prefix_reduce_kernel<T, Op, SEG, VEC, BIG><<<grid, kScanThreads, 0, stream>>>(p);
     DJB_POST_LAUNCH();
+}
+
+/// Small tiles keep every SM busy on small arrays; large tiles bound the tile rate on big ones
+static int scan_big_override() {
+    static int v = -2;
+    if (v == -2) {
+        const char *env = getenv("DRJIT_B200_SCAN_BIG"); // developer override: 0 / 1
+        v = env ? atoi(env) : -1;
+    }
+    return v;
+}
+
+template <typename T, typename Op, bool SEG, bool VEC>
+static void launch_prefix_variant(cudaStream_t stream, PrefixParams &p) {
+    const DeviceProps &dev = device_props();
+    bool big = (uint64_t) p.size >= (uint64_t) ScanGeom<T, VEC, true>::TILE * dev.sm_count * 8;
+    if (scan_big_override() >= 0) big = scan_big_override() != 0;
+    if (big) launch_prefix_geom<T, Op, SEG, VEC, true>(stream, p);
+    else     launch_prefix_geom<T, Op, SEG, VEC, false>(stream, p);
 }
 
 template <typename T, typename Op>

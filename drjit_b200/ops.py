@@ -11,6 +11,7 @@ tests read like the reference's own (citations relative to the reference tree):
 Arrays are 1-D contiguous torch CUDA tensors; torch supplies device memory and the current
 stream only. Every function goes through the C ABI (``_lib``); there is no torch fallback.
 """
+import builtins
 import ctypes
 import enum
 
@@ -211,7 +212,7 @@ def _pinned_offsets(bucket_count):
     need = 4 * bucket_count + 1
     buf = _pinned_cache.get("offsets")
     if buf is None or buf.numel() < need:
-        buf = torch.empty(max(need, 1 << 16), dtype=torch.int32).pin_memory()
+        buf = torch.empty(builtins.max(need, 1 << 16), dtype=torch.int32).pin_memory()
         _pinned_cache["offsets"] = buf
     return buf
 

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Times individual primitives with CUDA events (developer tool; not the bench contract).
+
+    python scripts/time_prims.py [prim ...] [--log2 N] [--reps R]
+prims: sum block_reduce dot scan scan64 compress compress01 compress99 mkperm mkperm256 scatter all
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import drjit_b200 as dr  # noqa: E402
+from drjit_b200 import ReduceOp, VarType, ops  # noqa: E402
+
+PEAK = 6451.8
+
+
+def timeit(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("prims", nargs="*", default=["all"])
+    ap.add_argument("--log2", type=int, default=None)
+    ap.add_argument("--reps", type=int, default=10)
+    a = ap.parse_args()
+    want = set(a.prims)
+    dev = "cuda"
+
+    def run(name, log2, bytes_per_elem, setup):
+        if "all" not in want and name not in want:
+            return
+        n = 1 << (a.log2 or log2)
+        fn = setup(n)
+        med, best = timeit(fn, a.reps)
+        gbs = n * bytes_per_elem / med / 1e6
+        print(f"{name:12s} n=2^{(a.log2 or log2):2d}  median {med:8.3f} ms  best {best:8.3f} ms  "
+              f"{gbs:8.1f} GB/s  {gbs / PEAK * 100:5.1f}% of measured peak  {n / med / 1e6:8.2f} Gelem/s", flush=True)
+
+    def s_sum(n):
+        x = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1)
+        return lambda: dr.sum(x)
+
+    def s_br(n):
+        x = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1)
+        out = torch.empty(n // 256, dtype=torch.float32, device=dev)
+        return lambda: ops.block_reduce(ReduceOp.Add, x, 256, out=out)
+
+    def s_dot(n):
+        x = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1)
+        y = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(y, 1, xor=5)
+        return lambda: dr.dot(x, y)
+
+    def s_scan(n):
+        x = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(x, 0)
+        out = torch.empty_like(x)
+        return lambda: ops.block_prefix_reduce(ReduceOp.Add, x, n, True, False, vt=VarType.UInt32, out=out)
+
+    def s_scan64(n):
+        x = torch.empty(n, dtype=torch.int64, device=dev); x.view(torch.int32)[::2] = 1
+        out = torch.empty_like(x)
+        return lambda: ops.block_prefix_reduce(ReduceOp.Add, x, n, True, False, vt=VarType.UInt64, out=out)
+
+    def s_scanseg(n):
+        x = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1)
+        out = torch.empty_like(x)
+        return lambda: ops.block_prefix_reduce(ReduceOp.Add, x, 1000, True, False, out=out)
+
+    def s_compress(thr):
+        def setup(n):
+            m = torch.empty(n, dtype=torch.uint8, device=dev); ops.fill_fmix32(m, 2, and_=thr)
+            out = torch.empty(n, dtype=torch.int32, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            return lambda: ops.compress_async(m, 0, out=out, count=cnt)
+        return setup
+
+    def s_mkperm(buckets):
+        def setup(n):
+            k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0, and_=buckets - 1)
+            perm = torch.empty_like(k); hist = torch.empty(buckets, dtype=torch.int32, device=dev)
+            return lambda: ops.mkperm_sharded(k, buckets, 0, perm=perm, hist=hist)
+        return setup
+
+    def s_scatter(n):
+        v = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(v, 1)
+        i = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(i, 0, xor=0x85EBCA6B, and_=(1 << 20) - 1)
+        bins = torch.zeros(1 << 20, dtype=torch.float32, device=dev)
+        return lambda: dr.scatter_add(bins, v, i)
+
+    run("sum", 28, 4, s_sum)
+    run("block_reduce", 28, 4 + 4 / 256, s_br)
+    run("dot", 28, 8, s_dot)
+    run("scan", 30, 8, s_scan)
+    run("scan64", 28, 16, s_scan64)
+    run("scanseg", 28, 8, s_scanseg)
+    run("compress", 30, 3, s_compress(128))
+    run("compress01", 30, 1 + 4 * 3 / 256, s_compress(3))
+    run("compress99", 30, 1 + 4 * 253 / 256, s_compress(253))
+    run("mkperm", 26, 12, s_mkperm(4096))
+    run("mkperm256", 26, 12, s_mkperm(256))
+    run("scatter", 28, 8, s_scatter)
+
+
+if __name__ == "__main__":
+    main()

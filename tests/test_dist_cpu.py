@@ -1,0 +1,146 @@
+"""Host-side logic of the sharded path under gloo, world_size 2, on CPU.
+
+drjit_b200.dist.Sharded takes the object that provides the shard-local primitives; here an
+oracle-backed CPU stand-in is injected (tests only) so that shard boundaries, the carry
+computation of the distributed scan, count/offset exchange and histogram combination are
+exercised end to end against the single-array oracle result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import capi  # noqa: E402
+
+_OPN = {1: "add", 2: "mul", 3: "min", 4: "max", 5: "and", 6: "or"}
+_VTN = {torch.int32: "u32", torch.float32: "f32", torch.uint8: "u8", torch.float64: "f64"}
+
+
+class OracleLocal:
+    """CPU stand-in for drjit_b200.ops (same call signatures, oracle arithmetic)."""
+
+    @staticmethod
+    def _np(x):
+        vt = _VTN[x.dtype]
+        return vt, x.numpy().view(capi.NP[vt])
+
+    @staticmethod
+    def _t(a, like):
+        return torch.from_numpy(np.ascontiguousarray(a).view(like.numpy().dtype))
+
+    def block_reduce(self, op, x, block_size, vt=None, out=None):
+        t, a = self._np(x)
+        return self._t(capi.block_reduce(t, _OPN[int(op)], a, block_size, acc64=True), x)
+
+    def dot(self, a, b):
+        return torch.tensor([float(capi.reduce_dot("f32", a.numpy(), b.numpy(), acc64=True))], dtype=torch.float32)
+
+    def block_prefix_reduce(self, op, x, block_size, exclusive=True, reverse=False, vt=None, out=None):
+        t, a = self._np(x)
+        return self._t(capi.block_prefix_reduce(t, _OPN[int(op)], a, block_size, exclusive, reverse), x)
+
+    def prefix_reduce_carry(self, op, x, exclusive=True, reverse=False, carry_in=None, total_out=None, vt=None, out=None):
+        t, a = self._np(x)
+        res = capi.block_prefix_reduce(t, _OPN[int(op)], a, a.size, exclusive, reverse)
+        if carry_in is not None:
+            res = (res + self._np(carry_in)[1][0]).astype(res.dtype)   # Add only (what the tests use)
+        return self._t(res, x)
+
+    def compress_async(self, mask, index_base=0, out=None, count=None):
+        idx = capi.compress(mask.numpy()) + np.uint32(index_base)
+        o = torch.zeros(mask.numel(), dtype=torch.int32)
+        o[:idx.size] = torch.from_numpy(idx.view(np.int32))
+        return o, torch.tensor([idx.size], dtype=torch.int32)
+
+    def mkperm_sharded(self, values, bucket_count, index_base=0, perm=None, hist=None):
+        keys = values.numpy().view(np.uint32)
+        p, _, _ = capi.block_mkperm(keys, keys.size, bucket_count)
+        h = np.bincount(keys, minlength=bucket_count).astype(np.int32)
+        return torch.from_numpy((p + np.uint32(index_base)).view(np.int32)), torch.from_numpy(h)
+
+    def scatter_reduce(self, op, target, value, index, active=None, mode=0, vt=None):
+        res = capi.scatter_reduce("f32", "add", target.numpy(), value.numpy(), index.numpy().view(np.uint32), acc64=True)
+        target.copy_(torch.from_numpy(res))
+        return target
+
+
+def _worker(rank, world, port, n):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from drjit_b200.dist import Sharded
+        from drjit_b200.ops import ReduceOp
+        sh = Sharded(rank=rank, world=world, group=dist.group.WORLD, local=OracleLocal())
+
+        lo, hi = sh.shard_range(n, align=256)
+        u = capi.fmix32(n)
+        ut = torch.from_numpy(u[lo:hi].view(np.int32).copy())
+
+        # sum / min / max
+        for op, name in ((ReduceOp.Add, "add"), (ReduceOp.Min, "min"), (ReduceOp.Max, "max")):
+            got = sh.reduce(op, ut).numpy().view(np.uint32)[0]
+            assert got == capi.block_reduce("u32", name, u, n)[0], name
+
+        # distributed exclusive prefix sum == slice of the single-array oracle scan (bit-exact)
+        got = sh.prefix_sum(ut).numpy().view(np.uint32)
+        exp = capi.block_prefix_reduce("u32", "add", u, n, True, False)[lo:hi]
+        assert np.array_equal(got, exp)
+
+        # compress: global indices, rank-order concatenation == oracle list
+        m = capi.mask_u8(n, 128)
+        out, counts = sh.compress(torch.from_numpy(m[lo:hi].copy()), lo)
+        exp_all = capi.compress(m)
+        start = sum(counts[:rank])
+        assert sum(counts) == exp_all.size
+        assert np.array_equal(out[:counts[rank]].numpy().view(np.uint32), exp_all[start:start + counts[rank]])
+
+        # mkperm: global histogram + rank-major stable order == oracle permutation
+        B = 37
+        keys = capi.fmix32(n) % np.uint32(B)
+        perm, hist, ghist = sh.mkperm(torch.from_numpy(keys[lo:hi].view(np.int32).copy()), B, lo)
+        assert np.array_equal(ghist.numpy(), np.bincount(keys, minlength=B))
+        gathered = [torch.zeros_like(hist) for _ in range(world)]
+        dist.all_gather(gathered, hist)
+        exp_perm, _, _ = capi.block_mkperm(keys, n, B)
+        bucket_start = np.cumsum(ghist.numpy()) - ghist.numpy()
+        local_start = np.cumsum(hist.numpy()) - hist.numpy()
+        for b in range(B):
+            before = sum(int(g[b]) for g in gathered[:rank])
+            mine = perm.numpy().view(np.uint32)[local_start[b]:local_start[b] + int(hist[b])]
+            assert np.array_equal(mine, exp_perm[bucket_start[b] + before: bucket_start[b] + before + int(hist[b])])
+
+        # scatter-add with all-reduced bins; dot
+        f = capi.unit_f32(n)
+        idx = capi.fmix32(n, xor=0x85EBCA6B, mask=63)
+        bins = sh.scatter_add(torch.zeros(64), torch.from_numpy(f[lo:hi].copy()),
+                              torch.from_numpy(idx[lo:hi].view(np.int32).copy()))
+        exp = capi.scatter_reduce("f32", "add", np.zeros(64, np.float32), f, idx, acc64=True)
+        assert np.allclose(bins.numpy(), exp, rtol=1e-5)
+        d = sh.dot(torch.from_numpy(f[lo:hi].copy()), torch.from_numpy(f[lo:hi].copy()))
+        assert abs(float(d[0]) - float(np.dot(f.astype(np.float64), f))) < 1e-4 * n
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [100_003, 4096])
+def test_sharded_primitives_gloo_world2(n):
+    port = 29500 + (os.getpid() % 500) + (1 if n == 4096 else 0)
+    mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_shard_bounds():
+    from drjit_b200.dist import shard_bounds
+    for n in (0, 1, 1000, 1 << 20, (1 << 20) + 7):
+        for world in (1, 2, 4, 8):
+            for align in (1, 256, 1024):
+                b = shard_bounds(n, world, align)
+                assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+                assert all(x <= y for x, y in zip(b, b[1:]))
+                assert all(x % align == 0 or x == n for x in b)
