@@ -8,8 +8,9 @@ One "step" = one pass of the primitive suite over synthetic fmix32 inputs reside
     compress 2^30 (50 % dense) | block_mkperm 2^26 keys x 4096 buckets | scatter_add f32 2^28 -> 2^20 bins
 
 value = algorithmic bytes of the whole suite / device time of one step (GB/s), inputs larger
-than L2 (no flush needed). With --gpus N the same TOTAL arrays are sharded over N ranks
-("strong" scaling); NCCL is used only for the combine messages.
+than L2 (no flush needed). With --gpus N every rank holds one shard of the sizes above (the
+global arrays are N times larger: "weak" scaling, rank r owns the contiguous index range
+[r*n, (r+1)*n)); NCCL is used only for the combine messages.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
 
@@ -159,7 +160,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -171,7 +172,8 @@ def run_reference_arm(args):
 def workload_config(args):
     return {"workload": "primitive suite: sum/block_reduce(256)/dot f32 2^28, exclusive prefix_sum u32 2^30, "
                         "compress u8 2^30 (50%), block_mkperm 2^26 x 4096 buckets, scatter_add f32 2^28 -> 2^20 bins",
-            "sharding": f"contiguous index ranges over {args.gpus} rank(s), NCCL only for combine messages",
+            "sharding": f"{args.gpus} rank(s), each owning one contiguous shard of the sizes above (global arrays "
+                        f"are {args.gpus}x larger; compress indices are global mod 2^32); NCCL only for combine messages",
             "l2": "every input array > 126 MB L2 (no flush needed)",
             "scale_shift": args.scale}
 
@@ -221,8 +223,9 @@ def main():
     bins = 1 << max(4, BINS_LOG2 - S)
 
     # ---- shard-resident synthetic inputs (generated on the device) -------------------------
-    def shard(n, align=1024):
-        return sh.shard_range(n, align)
+    def shard(n):
+        """Weak scaling: rank r owns elements [r*n, (r+1)*n) of a global array of world*n entries."""
+        return rank * n, (rank + 1) * n
 
     lo_f, hi_f = shard(size["sum_f32"])
     x = torch.empty(hi_f - lo_f, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1, start=lo_f)
@@ -259,10 +262,10 @@ def main():
         results["scan"] = sh.prefix_sum(u, vt=VarType.UInt32, out=u_out)
 
     def p_compress():
-        results["count"] = sh.compress(mask, lo_m, out=c_out)
+        results["count"] = sh.compress(mask, lo_m & 0xFFFFFFFF, out=c_out)
 
     def p_mkperm():
-        results["mkperm"] = sh.mkperm(keys, BUCKETS, lo_k, perm=perm)
+        results["mkperm"] = sh.mkperm(keys, BUCKETS, lo_k & 0xFFFFFFFF, perm=perm)
 
     def p_scatter():
         bins_t.zero_()
@@ -271,7 +274,7 @@ def main():
     prims = [("sum_f32", p_sum), ("block_reduce256_f32", p_block_reduce), ("dot_f32", p_dot),
              ("prefix_sum_u32", p_prefix), ("compress_u8", p_compress), ("mkperm_4096", p_mkperm),
              ("scatter_add_f32", p_scatter)]
-    total_bytes = sum(size[n] * bpe[n] for n, _ in prims)
+    total_bytes = world * sum(size[n] * bpe[n] for n, _ in prims)   # all ranks
 
     def barrier():
         if world > 1:
@@ -318,9 +321,9 @@ def main():
 
     primitives = {}
     for (name, _), ms in zip(prims, per_ms):
-        gbs = size[name] * bpe[name] / (ms * 1e-3) / 1e9
-        primitives[name] = {"elements": size[name], "ms": round(ms, 4), "GBps": round(gbs, 1),
-                            "Gelem_per_s": round(size[name] / (ms * 1e-3) / 1e9, 2),
+        gbs = world * size[name] * bpe[name] / (ms * 1e-3) / 1e9
+        primitives[name] = {"elements": world * size[name], "ms": round(ms, 4), "GBps": round(gbs, 1),
+                            "Gelem_per_s": round(world * size[name] / (ms * 1e-3) / 1e9, 2),
                             "frac_of_peak_per_gpu": round(gbs / (peak * world), 4)}
 
     # ---- end-to-end: host buffers through the public API, copies inside the timed region ----
@@ -338,10 +341,10 @@ def main():
 
     # dominant kernel for the roofline object: the single-pass scan (largest share of the step)
     scan = primitives["prefix_sum_u32"]
-    roofline = {"bound": "hbm", "kernel": "prefix_reduce_kernel<u32,Add> (exclusive prefix_sum, 2^30/N elements per rank)",
+    roofline = {"bound": "hbm", "kernel": "prefix_reduce_kernel<u32,Add> (exclusive prefix_sum, 2^30 elements per rank)",
                 "achieved": scan["GBps"] / world, "peak": peak, "unit": "GB/s",
                 "frac": round(scan["GBps"] / world / peak, 4), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": size["prefix_sum_u32"] * 8.0 / world}
+                "algorithmic_bytes_per_launch": size["prefix_sum_u32"] * 8.0}
 
     cpu_baseline = None
     if not args.no_cpu:
@@ -358,7 +361,7 @@ def main():
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
         "config": workload_config(args), "frac_of_hbm_peak": round(value / (peak * world), 4),
         "primitives": primitives, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
