@@ -330,6 +330,173 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
 }
 
 // ---------------------------------------------------------------------------
+//  Tile-staged fast path (single sorting group, bucket_count <= 8192, large inputs)
+// ---------------------------------------------------------------------------
+//  The row-per-warp design above keeps one write cursor per (warp, bucket): with 4096 buckets
+//  and ~1900 rows that is 7.9 M cursors advancing 4 bytes at a time, the partially written
+//  sectors do not survive in L2 and every 4-byte store costs a 32-byte DRAM read-modify-write
+//  (measured: 1.93 GB written + 1.96 GB read for a 268 MB permutation, profiles/r1a). Here the
+//  array is cut into tiles of 16 Ki keys that all CTAs walk in the same order, so that at any
+//  time the whole chip writes into a narrow moving window of every bucket (a few KiB) that L2
+//  merges into full lines:
+//    K1 tile histogram : CTA c counts a contiguous chunk of tiles in shared memory (8.6 shared
+//                        atomics/clk/SM measured); before each tile it snapshots the running
+//                        counts -> tile_off[tile][bucket] (exclusive prefix inside the chunk).
+//    K2 column scan over the C chunk totals + bucket scan (kernels above).
+//    K3 tile scatter   : per tile: rank = shared atomicAdd (one per key), exclusive scan of the
+//                        tile histogram, keys re-ordered by bucket in shared memory, then
+//                        written out as runs: consecutive threads store consecutive entries.
+//  Ranks come from atomics, so the order inside a bucket is not the input order (same contract
+//  as the reference's "small"/"large" variants, jit.h:2404-2406); bucket boundaries, the offsets
+//  table and per-bucket contents are exact.
+constexpr uint32_t kTileThreads = 512;
+constexpr uint32_t kTileKeys = 16384;                      // keys per tile (ranks fit 16 bits)
+constexpr uint32_t kTileKeysPerThread = kTileKeys / kTileThreads;
+constexpr uint32_t kTileMaxBuckets = 8192;
+
+struct MkpermTileParams {
+    const uint32_t *values;
+    uint32_t *perm;
+    uint32_t *tile_off;      // [tiles][buckets] exclusive prefix of the tile inside its chunk
+    uint32_t *rows;          // [chunks][buckets] chunk totals -> (column scan) exclusive chunk offsets
+    const uint32_t *bucket_start; // [buckets] after the bucket scan
+    uint32_t size, bucket_count, tiles, tiles_per_chunk, index_base;
+    uint8_t vec;
+};
+
+/// Loads the keys of one tile into registers (clamped to the last bucket: out-of-range keys are
+/// undefined behaviour in the reference; here they can at least not corrupt shared memory).
+/// local index of key (k, e): VEC: ((k * threads + tid) * 4 + e), else k * threads + tid.
+__device__ __forceinline__ void tile_load_keys(const MkpermTileParams &p, uint64_t tile_base, uint32_t n_tile,
+                                               uint32_t (&key)[kTileKeysPerThread]) {
+    const uint32_t tid = threadIdx.x, last = p.bucket_count - 1;
+    if (p.vec && n_tile == kTileKeys) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(p.values + tile_base);
+        #pragma unroll
+        for (uint32_t k = 0; k < kTileKeysPerThread / 4; ++k) {
+            const Vec16<uint32_t> t = ld_stream<uint32_t>(v + k * kTileThreads + tid);
+            #pragma unroll
+            for (uint32_t e = 0; e < 4; ++e) key[k * 4 + e] = min(t.v[e], last);
+        }
+    } else {
+        #pragma unroll
+        for (uint32_t k = 0; k < kTileKeysPerThread; ++k) {
+            const uint32_t i = k * kTileThreads + tid;
+            key[k] = i < n_tile ? min(__ldg(p.values + tile_base + i), last) : 0xffffffffu;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2)
+mkperm_tile_hist_kernel(const MkpermTileParams p) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *hist = smem;                                  // running counts of this chunk
+    const uint32_t tid = threadIdx.x, B = p.bucket_count;
+    for (uint32_t b = tid; b < B; b += kTileThreads) hist[b] = 0;
+
+    const uint32_t first = blockIdx.x * p.tiles_per_chunk,
+                   end = min(first + p.tiles_per_chunk, p.tiles);
+    for (uint32_t tile = first; tile < end; ++tile) {
+        const uint64_t tile_base = (uint64_t) tile * kTileKeys;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) kTileKeys, (uint64_t) p.size - tile_base);
+        uint32_t key[kTileKeysPerThread];
+        tile_load_keys(p, tile_base, n_tile, key);          // loads in flight across the barrier
+        __syncthreads();                                    // previous tile's atomics are done
+        uint32_t *dst = p.tile_off + (size_t) tile * B;
+        for (uint32_t b = tid; b < B; b += kTileThreads) dst[b] = hist[b];
+        __syncthreads();
+        #pragma unroll
+        for (uint32_t k = 0; k < kTileKeysPerThread; ++k)
+            if (key[k] != 0xffffffffu) atomicAdd(hist + key[k], 1u);
+    }
+    __syncthreads();
+    uint32_t *row = p.rows + (size_t) blockIdx.x * B;
+    for (uint32_t b = tid; b < B; b += kTileThreads) row[b] = hist[b];
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2)
+mkperm_tile_scatter_kernel(const MkpermTileParams p) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t B = p.bucket_count;
+    uint32_t *hist = smem;               // [B] tile counts -> exclusive tile-local starts
+    uint32_t *delta = smem + B;          // [B] global position of the bucket's run minus its local start
+    uint32_t *sorted = smem + 2 * B;     // [kTileKeys] (bucket << 16 | local index), ordered by bucket
+    __shared__ uint32_t warp_sum[kTileThreads / 32];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t per_thread = (B + kTileThreads - 1) / kTileThreads;    // bins per thread (contiguous)
+
+    for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const uint64_t tile_base = (uint64_t) tile * kTileKeys;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) kTileKeys, (uint64_t) p.size - tile_base);
+        const bool vec = p.vec && n_tile == kTileKeys;
+
+        uint32_t key[kTileKeysPerThread];
+        tile_load_keys(p, tile_base, n_tile, key);
+        for (uint32_t b = tid; b < B; b += kTileThreads) hist[b] = 0;
+        __syncthreads();
+
+        // rank inside (tile, bucket): one shared-memory atomic per key
+        #pragma unroll
+        for (uint32_t k = 0; k < kTileKeysPerThread; ++k)
+            if (key[k] != 0xffffffffu)
+                key[k] = (key[k] << 16) | atomicAdd(hist + key[k], 1u);
+        __syncthreads();
+
+        // exclusive scan of the tile histogram; thread t owns bins [t * per_thread, ...)
+        {
+            const uint32_t b0 = tid * per_thread;
+            uint32_t sum = 0;
+            for (uint32_t j = 0; j < per_thread; ++j)
+                if (b0 + j < B) sum += hist[b0 + j];
+            uint32_t incl = sum;
+            #pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const uint32_t t = shfl_up(incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) warp_sum[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            #pragma unroll
+            for (uint32_t w = 0; w < kTileThreads / 32; ++w)
+                if (w < warp) wbase += warp_sum[w];
+            uint32_t run = wbase + incl - sum;
+            const uint32_t chunk = tile / p.tiles_per_chunk;
+            const uint32_t *toff = p.tile_off + (size_t) tile * B, *crow = p.rows + (size_t) chunk * B;
+            for (uint32_t j = 0; j < per_thread; ++j) {
+                const uint32_t b = b0 + j;
+                if (b < B) {
+                    const uint32_t c = hist[b];
+                    hist[b] = run;
+                    delta[b] = p.bucket_start[b] + crow[b] + toff[b] - run;
+                    run += c;
+                }
+            }
+        }
+        __syncthreads();
+
+        // re-order by bucket in shared memory
+        #pragma unroll
+        for (uint32_t k = 0; k < kTileKeysPerThread; ++k) {
+            if (key[k] != 0xffffffffu) {
+                const uint32_t b = key[k] >> 16, rank = key[k] & 0xffffu;
+                const uint32_t local = vec ? ((k / 4) * kTileThreads + tid) * 4 + (k & 3u) : k * kTileThreads + tid;
+                sorted[hist[b] + rank] = (b << 16) | local;
+            }
+        }
+        __syncthreads();
+
+        // runs of equal buckets are contiguous in `sorted` and in `perm`: coalesced stores
+        const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
+        for (uint32_t j = tid; j < n_tile; j += kTileThreads) {
+            const uint32_t e = sorted[j];
+            p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 //  Host side
 // ---------------------------------------------------------------------------
 static MkpermMode pick_mode(uint32_t bucket_count, uint32_t smem_budget, uint32_t &warps) {
@@ -375,6 +542,7 @@ static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads
     DJB_POST_LAUNCH();
 }
 
+
 static cudaEvent_t mkperm_event() {
     static thread_local cudaEvent_t ev = nullptr;
     static thread_local int ev_device = -1;
@@ -384,6 +552,92 @@ static cudaEvent_t mkperm_event() {
         ev_device = device;
     }
     return ev;
+}
+
+/// Developer override for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path
+static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_count) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *env = getenv("DRJIT_B200_MKPERM_TILES");
+        enabled = env ? atoi(env) != 0 : 1;
+    }
+    const uint64_t tiles = ceil_div64(size, kTileKeys);
+    return enabled && n_groups == 1 && bucket_count <= kTileMaxBuckets && size >= (1u << 18) &&
+           tiles * bucket_count * 4 <= ((uint64_t) 2 << 30);
+}
+
+static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
+                             uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
+                             uint32_t *offsets, uint32_t *hist_out) {
+    const DeviceProps &dev = device_props();
+    MkpermTileParams t{};
+    t.values = values; t.perm = perm; t.size = size; t.bucket_count = bucket_count;
+    t.index_base = index_base;
+    t.tiles = (uint32_t) ceil_div64(size, kTileKeys);
+    t.vec = ((uintptr_t) values % 16) == 0;
+
+    const uint32_t hist_smem = bucket_count * 4,
+                   scatter_smem = bucket_count * 8 + kTileKeys * 4;
+    uint32_t chunks = std::min(t.tiles, dev.sm_count * 2);
+    t.tiles_per_chunk = ceil_div(t.tiles, chunks);
+    chunks = ceil_div(t.tiles, t.tiles_per_chunk);
+
+    // the column / bucket scan kernels work on MkpermParams: one group, `chunks` rows
+    MkpermParams p{};
+    p.values = values; p.perm = perm; p.size = size; p.block_size = size;
+    p.bucket_count = bucket_count; p.n_groups = 1; p.rows_per_group = chunks;
+
+    Scratch scratch(stream);
+    const size_t off_bytes = (size_t) t.tiles * bucket_count * 4,
+                 rows_bytes = (size_t) chunks * bucket_count * 4,
+                 totals_bytes = (size_t) bucket_count * 4;
+    auto r256 = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+    scratch.reserve(r256(off_bytes) + r256(rows_bytes) + r256(totals_bytes) + 512);
+    t.tile_off = (uint32_t *) scratch.device(off_bytes);
+    t.rows = p.rows = (uint32_t *) scratch.device(rows_bytes);
+    p.totals = (uint32_t *) scratch.device(totals_bytes);
+    t.bucket_start = p.totals;
+
+    const bool want_table = offsets != nullptr;
+    uint32_t *offsets_dev = nullptr, *unique_dev = nullptr;
+    uint32_t *pinned = scratch.pinned_words();
+    if (want_table) {
+        cudaError_t rv = cudaHostGetDevicePointer((void **) &offsets_dev, offsets, 0);
+        if (rv != cudaSuccess) {
+            (void) cudaGetLastError();
+            raise(DRJIT_B200_EINVAL, "jit_block_mkperm(): 'offsets' must point to host-pinned "
+                                     "(device-mapped) memory!");
+        }
+        DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &unique_dev, pinned + 1, 0));
+    }
+
+    static bool configured = false;
+    if (!configured) {
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int) (kTileMaxBuckets * 4)));
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int) (kTileMaxBuckets * 8 + kTileKeys * 4)));
+        configured = true;
+    }
+
+    mkperm_tile_hist_kernel<<<chunks, kTileThreads, hist_smem, stream>>>(t);
+    DJB_POST_LAUNCH();
+    const uint32_t col_tiles = ceil_div(bucket_count, 32);
+    mkperm_column_scan_kernel<<<col_tiles, 256, 0, stream>>>(p, col_tiles);
+    DJB_POST_LAUNCH();
+    mkperm_bucket_scan_kernel<<<1, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out);
+    DJB_POST_LAUNCH();
+    cudaEvent_t ev = want_table ? mkperm_event() : nullptr;
+    if (ev)
+        DJB_CUDA_CHECK(cudaEventRecord(ev, stream));       // cuda_ts.cpp:953 (before the scatter pass)
+    const uint32_t grid = std::min(t.tiles, dev.sm_count * (scatter_smem <= 100 * 1024 ? 2u : 1u));
+    mkperm_tile_scatter_kernel<<<grid, kTileThreads, scatter_smem, stream>>>(t);
+    DJB_POST_LAUNCH();
+
+    if (!want_table)
+        return 0;
+    DJB_CUDA_CHECK(cudaEventSynchronize(ev));              // cuda_ts.cpp:964-967
+    return pinned[1];
 }
 
 /// Shared implementation. offsets: pinned host table (may be NULL). hist_out: optional device
@@ -405,6 +659,9 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.values = values; p.perm = perm; p.size = size; p.block_size = block_size;
     p.bucket_count = bucket_count; p.index_base = index_base;
     p.n_groups = ceil_div(size, block_size);
+
+    if (use_tile_path(p.n_groups, size, bucket_count))
+        return mkperm_tiles(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
 
     uint32_t warps = 32;
     const uint32_t smem_budget = dev.smem_optin - 1024;

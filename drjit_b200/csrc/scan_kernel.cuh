@@ -1,0 +1,560 @@
+/*
+ * scan_kernel.cuh -- device side of the single-pass (segmented) prefix reduction.
+ * Host-side dispatch: prefix_reduce.cu; geometry sweep: scripts/sweep_scan.cu.
+ *
+ * One persistent kernel scans the flat array tile by tile. CTA c processes tiles c, c + G,
+ * c + 2G, ... (G = grid size); the grid is launched cooperatively, so all CTAs are co-resident
+ * and the look-back always makes progress (the lowest unfinished tile belongs to a running CTA
+ * that is working on it). Tiles are chained with a decoupled look-back (Merrill & Garland) in
+ * which warp 0 inspects 256 predecessor descriptors per round (8 loads in flight per lane):
+ * the sustainable tile rate of a look-back is window / L2 round trip, and a 64-wide window
+ * (~60 tiles/us measured) is below what HBM3e delivers (profiles/r1_scan_sweep.md).
+ * Each thread owns ROWS 128-bit units in a warp-striped arrangement, so global stores are
+ * coalesced STG.128 without a shared-memory transpose.
+ *
+ * STAGES > 0: full tiles are fetched by `cp.async.bulk` (TMA, tma.cuh) into a ring of STAGES
+ * shared-memory buffers. A stage is refilled as soon as its tile has been moved to registers,
+ * i.e. *before* the tile's scan / store phases, so every CTA keeps STAGES tiles in flight no
+ * matter which phase it is in. The static schedule is what makes this possible: prefetching
+ * does not delay the publication of any tile's aggregate.
+ * STAGES >= 2, unsegmented ("CHAIN"): the CTA gets a ninth warp that owns the whole chain
+ * protocol. The eight scan warps reduce a tile straight from shared memory as soon as its bulk
+ * copy has landed -- STAGES-1 iterations before they scan it -- and hand the eight partials to
+ * the chain warp through an mbarrier; the chain warp publishes the aggregate, performs the
+ * look-back, publishes the inclusive prefix and leaves the tile's carry in a ring. By the time
+ * the scan warps reach the tile its carry has long been computed: neither the L2 round trips of
+ * the look-back nor a late bulk copy elsewhere on the chip stall them (profiles/r1_scan_sweep.md).
+ * STAGES == 0: direct LDG path (unaligned arrays, element-wise loads when !VEC).
+ *
+ * `block_size` only changes where the running value is reset: the scan is segmented with heads
+ * at multiples of `block_size`; a tile that contains a head publishes its post-head aggregate
+ * as a complete prefix immediately, so short blocks never form a dependency chain. `reverse`
+ * mirrors tile and element order; `exclusive` shifts the result by one element at store time.
+ *
+ * Reference: resources/block_prefix_reduce.cuh:46-214 (one element per thread, 10-step
+ * Hillis-Steele scan with 20 barriers per 1024 elements, every warp spins in the look-back).
+ */
+#pragma once
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace djb {
+
+constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanWarps = kScanThreads / 32;
+constexpr uint32_t kScanFetchTid = kScanThreads - 32;   // lane 0 of the last scan warp issues the TMA copies
+constexpr uint32_t kLookbackLoads = 10;                 // descriptors per lane and round (window = 320)
+
+enum : uint32_t { kInvalid = 0, kAggregate = 1, kPrefix = 2 };
+
+// ---------------------------------------------------------------------------
+//  Tile descriptors
+// ---------------------------------------------------------------------------
+template <typename A, size_t Size = sizeof(A)> struct TileState;
+
+/// 4-byte accumulators: {value, status} packed into one 64-bit word (single-copy atomic)
+template <typename A> struct TileState<A, 4> {
+    uint64_t *words;
+    static size_t bytes(uint32_t tiles) { return (size_t) tiles * 8; }
+    __host__ __device__ void bind(void *base, uint32_t) { words = (uint64_t *) base; }
+    __device__ __forceinline__ void publish(uint32_t tile, uint32_t status, A value) {
+        uint32_t bits;
+        memcpy(&bits, &value, 4);
+        st_relaxed_u64(words + tile, ((uint64_t) bits << 32) | status);
+    }
+    __device__ __forceinline__ void load(uint32_t tile, uint32_t &status, A &value) {
+        const uint64_t w = ld_relaxed_u64(words + tile);
+        status = (uint32_t) w;
+        const uint32_t bits = (uint32_t) (w >> 32);
+        memcpy(&value, &bits, 4);
+    }
+};
+
+/// 8-byte accumulators: separate value arrays guarded by a status word (release/acquire)
+template <typename A> struct TileState<A, 8> {
+    uint32_t *status_words;
+    uint64_t *aggregates, *prefixes;
+    static size_t bytes(uint32_t tiles) { return ((size_t) tiles * 4 + 255) / 256 * 256 + (size_t) tiles * 16; }
+    __host__ __device__ void bind(void *base, uint32_t tiles) {
+        status_words = (uint32_t *) base;
+        aggregates = (uint64_t *) ((uint8_t *) base + ((size_t) tiles * 4 + 255) / 256 * 256);
+        prefixes = aggregates + tiles;
+    }
+    __device__ __forceinline__ void publish(uint32_t tile, uint32_t status, A value) {
+        uint64_t bits;
+        memcpy(&bits, &value, 8);
+        st_relaxed_u64((status == kPrefix ? prefixes : aggregates) + tile, bits);
+        st_release_u32(status_words + tile, status);
+    }
+    __device__ __forceinline__ void load(uint32_t tile, uint32_t &status, A &value) {
+        status = ld_acquire_u32(status_words + tile);
+        uint64_t bits = 0;
+        if (status != kInvalid)
+            bits = ld_relaxed_u64((status == kPrefix ? prefixes : aggregates) + tile);
+        memcpy(&value, &bits, 8);
+    }
+};
+
+struct PrefixParams {
+    const void *in;
+    void *out;
+    void *state;            // tile descriptors (zero on entry)
+    const void *carry_in;   // optional device scalar (sharded scans)
+    void *total_out;        // optional device scalar
+    uint64_t magic;         // floor(2^64 / block_size) (+ 1 unless block_size is a power of two)
+    uint32_t size, block_size, tiles;
+    uint8_t exclusive, reverse, in_place;
+    uint8_t debug;          // timing experiments only (scripts/sweep_scan.cu): 1 = skip look-back, 2 = skip stores
+};
+
+/// Tile geometry. A "unit" is what one thread moves at once (a 128-bit vector, or one element
+/// on the unaligned path); a thread owns ROWS units. R = units per thread for 4-byte types;
+/// narrower types use fewer units so that the number of accumulator registers (elements per
+/// thread) stays the same.
+template <typename T, bool VEC, uint32_t R> struct ScanGeom {
+    static constexpr uint32_t V = VEC ? 16 / sizeof(T) : 1;
+    static constexpr uint32_t ROWS_ = !VEC ? R : (V >= 16 ? R / 4 : (V == 8 ? R / 2 : R));
+    static constexpr uint32_t ROWS = ROWS_ == 0 ? 1 : ROWS_;
+    static constexpr uint32_t TILE = kScanThreads * ROWS * V;          // elements
+    static constexpr uint32_t TILE_BYTES = TILE * sizeof(T);
+};
+
+/// The chain warp exists for unsegmented scans with at least two TMA stages
+template <bool SEG, uint32_t STAGES, bool CHAINW> struct ScanRoles {
+    static constexpr bool EARLY = STAGES >= 2 && !SEG;      // aggregates published when the copy lands
+    static constexpr bool CHAIN = EARLY && CHAINW;          // ... and a dedicated chain warp
+    static constexpr uint32_t THREADS = kScanThreads + (CHAIN ? 32 : 0);
+};
+
+/// Barrier among the eight scan warps only (the chain warp never takes part)
+__device__ __forceinline__ void scan_warps_sync() {
+    asm volatile("bar.sync 1, %0;" :: "n"(kScanThreads) : "memory");
+}
+
+/// Decoupled look-back executed by one full warp: reduction of all tiles before `tile`
+/// (tile >= 1). Each round inspects kLookbackLoads x 32 predecessors with all descriptor loads
+/// of the round in flight together; windows of 32 are then folded nearest first, and only a
+/// window that still holds an unpublished descriptor is polled again.
+template <typename Op, typename A>
+__device__ __forceinline__ A scan_lookback(TileState<A> &state, uint32_t tile, uint32_t lane) {
+    const A ident = Op::template identity<A>();
+    A excl = ident;
+    int32_t pred = (int32_t) tile - 1 - (int32_t) lane;
+    // folds one window of 32 descriptors into `excl`; true once a complete prefix was found
+    auto consume = [&](int32_t first, uint32_t status, A value) -> bool {
+        while (__any_sync(kFullMask, status == kInvalid)) {
+            __nanosleep(20);
+            if (first >= 0)
+                state.load((uint32_t) first, status, value);
+        }
+        const uint32_t done = __ballot_sync(kFullMask, status == kPrefix);
+        // nearest predecessor holding a complete prefix (lowest lane)
+        const uint32_t stop = done ? (uint32_t) __ffs(done) - 1 : 31u;
+        A contrib = lane <= stop ? value : ident;
+        contrib = WarpReduce<Op, A>::template run<32>(contrib);
+        excl = Op::template apply<A>(contrib, excl);
+        return done != 0;
+    };
+    while (true) {
+        // lanes past the start of the array act like a finished tile holding the identity
+        uint32_t status[kLookbackLoads];
+        A value[kLookbackLoads];
+        #pragma unroll
+        for (uint32_t j = 0; j < kLookbackLoads; ++j) {
+            status[j] = kPrefix; value[j] = ident;
+            const int32_t idx = pred - 32 * (int32_t) j;
+            if (idx >= 0) state.load((uint32_t) idx, status[j], value[j]);
+        }
+        bool found = false;
+        #pragma unroll
+        for (uint32_t j = 0; j < kLookbackLoads; ++j) {
+            if (!found && consume(pred - 32 * (int32_t) j, status[j], value[j]))
+                found = true;
+        }
+        if (found) break;
+        pred -= 32 * (int32_t) kLookbackLoads;
+    }
+    return excl;
+}
+
+template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS, bool CHAINW = true>
+__global__ void __launch_bounds__((ScanRoles<SEG, STAGES, CHAINW>::THREADS), MIN_CTAS)
+prefix_reduce_kernel(const PrefixParams p) {
+    using A = acc_t<T>;
+    using Geom = ScanGeom<T, VEC, R>;
+    constexpr uint32_t V = Geom::V;         // elements per unit
+    constexpr uint32_t ROWS = Geom::ROWS;   // units per thread
+    constexpr uint32_t TILE = Geom::TILE;
+    constexpr bool STAGED = STAGES > 0;
+    constexpr bool EARLY = ScanRoles<SEG, STAGES, CHAINW>::EARLY;
+    constexpr bool CHAIN = ScanRoles<SEG, STAGES, CHAINW>::CHAIN;
+    constexpr uint32_t NS = STAGED ? STAGES : 1;
+    static_assert(!STAGED || VEC, "staged tiles need the 128-bit path");
+    const A ident = Op::template identity<A>();
+
+    extern __shared__ __align__(128) uint8_t stage_mem[];   // STAGES x TILE_BYTES
+    __shared__ uint64_t full_bar[NS];       // TMA: tile has landed in its stage
+    __shared__ uint64_t early_bar[NS];      // CHAIN: the 8 partial aggregates of a tile are in early_val
+    __shared__ uint64_t carry_bar[NS];      // CHAIN: the tile's carry is in carry_ring
+    __shared__ A early_val[NS][kScanWarps];
+    __shared__ A carry_ring[NS];
+    __shared__ A agg_ring[NS];              // chain warp private
+    __shared__ A warp_val[kScanWarps];
+    __shared__ uint32_t warp_flag[kScanWarps];
+    __shared__ A carry_smem;
+
+    const T *in = (const T *) p.in;
+    T *out = (T *) p.out;
+    TileState<A> state;
+    state.bind(p.state, p.tiles);
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t size = p.size, bs = p.block_size;
+    const bool rev = p.reverse;
+
+    // residue helper: x mod block_size for x <= 2^32 (exact)
+    auto mod_bs = [&](uint64_t x) -> uint32_t {
+        const uint64_t q = __umul64hi(x, p.magic);
+        return (uint32_t) (x - q * bs);
+    };
+
+    // ---- tile acquisition (static round-robin schedule) ---------------------------------
+    uint64_t policy = 0;
+    auto tile_of = [&](uint32_t k) -> uint64_t { return (uint64_t) blockIdx.x + (uint64_t) k * gridDim.x; };
+    auto tile_is_staged = [&](uint64_t tile) -> bool {
+        return STAGED && tile < p.tiles && (tile + 1) * TILE <= size;
+    };
+    // fetch thread only: start the bulk copy of `tile` into stage s
+    auto issue = [&](uint32_t s, uint64_t tile) {
+        if (tile_is_staged(tile)) {
+            const uint64_t first = rev ? (uint64_t) size - (tile + 1) * TILE : tile * TILE;
+            mbar_expect_tx(&full_bar[s], Geom::TILE_BYTES);
+            bulk_load(stage_mem + (size_t) s * Geom::TILE_BYTES, in + first, Geom::TILE_BYTES, &full_bar[s], policy);
+        }
+    };
+    if constexpr (STAGED) {
+        if (tid == kScanFetchTid) {
+            #pragma unroll
+            for (uint32_t s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&early_bar[s], kScanWarps);
+                mbar_init(&carry_bar[s], 1);
+            }
+            fence_proxy_async();
+            policy = policy_evict_first();
+            #pragma unroll
+            for (uint32_t s = 0; s < STAGES; ++s) issue(s, tile_of(s));
+        }
+        __syncthreads();
+    }
+
+    // ===================================================================================
+    //  Chain warp: aggregate -> look-back -> inclusive prefix -> carry, one tile after another
+    // ===================================================================================
+    if constexpr (CHAIN) {
+        if (warp == kScanWarps) {
+            // Step i publishes the aggregate of the CTA's i-th tile (its partials arrive when the
+            // scan warps *start* iteration i-(STAGES-1)) and then resolves the carry of tile
+            // i-(STAGES-1), which the scan warps need at the *end* of that iteration. Aggregates
+            // are therefore STAGES-1 iterations old when a look-back reads them, and the
+            // look-back's L2 round trips overlap the scan warps' own work on the tile.
+            // With three or more stages the carry is resolved one iteration earlier still (LAG =
+            // STAGES-2), which takes the look-back off the scan warps' critical path entirely.
+            constexpr uint32_t LAG = STAGES >= 3 ? STAGES - 2 : STAGES - 1;
+            const uint64_t last = p.tiles - 1;
+            const uint32_t n_cta = blockIdx.x > last ? 0u : (uint32_t) ((last - blockIdx.x) / gridDim.x) + 1u;
+            for (uint32_t step = 0; step < n_cta + LAG; ++step) {
+                if (step < n_cta && tile_is_staged(tile_of(step))) {
+                    const uint32_t s = step % NS;
+                    mbar_wait(&early_bar[s], (step / NS) & 1u);
+                    A agg = lane < kScanWarps ? early_val[s][lane] : ident;
+                    agg = WarpReduce<Op, A>::template run<32>(agg);
+                    if (lane == 0) {
+                        agg_ring[s] = agg;
+                        if (tile_of(step) != 0)
+                            state.publish((uint32_t) tile_of(step), kAggregate, agg);
+                    }
+                }
+                if (step >= LAG) {
+                    const uint32_t k = step - LAG, s = k % NS;
+                    const uint64_t t64 = tile_of(k);
+                    const uint32_t tile = (uint32_t) t64;
+                    A excl = ident;
+                    if (tile == 0) {
+                        if (p.carry_in) excl = to_acc<A>(*(const T *) p.carry_in);
+                    } else if (!(p.debug & 1)) {
+                        excl = scan_lookback<Op, A>(state, tile, lane);
+                    }
+                    if (lane == 0) {
+                        if (tile_is_staged(t64))       // (only a ragged last tile is not staged)
+                            state.publish(tile, kPrefix, Op::template apply<A>(excl, agg_ring[s]));
+                        carry_ring[s] = excl;
+                        mbar_arrive(&carry_bar[s]);
+                    }
+                }
+                __syncwarp();
+            }
+            return;
+        }
+    }
+
+    // CHAIN, scan warps: per-warp partial aggregate of this CTA's k-th tile, read from its stage
+    // as soon as it has landed and handed to the chain warp
+    auto early_reduce = [&](uint32_t k) {
+        const uint64_t t64 = tile_of(k);
+        if (!tile_is_staged(t64))
+            return;
+        const uint32_t s = k % NS;
+        mbar_wait(&full_bar[s], (k / NS) & 1u);
+        const uint8_t *src = stage_mem + (size_t) s * Geom::TILE_BYTES;
+        A acc = ident;
+        #pragma unroll
+        for (uint32_t r = 0; r < ROWS; ++r) {
+            Vec16<T> v;
+            *reinterpret_cast<uint4 *>(&v) = lds128(src + ((warp * ROWS + r) * 32 + lane) * 16);
+            #pragma unroll
+            for (uint32_t e = 0; e < V; ++e)
+                acc = Op::template apply<A>(acc, to_acc<A>(v.v[e]));
+        }
+        acc = WarpReduce<Op, A>::template run<32>(acc);
+        if (lane == 0) {
+            early_val[s][warp] = acc;
+            if constexpr (CHAIN) mbar_arrive(&early_bar[s]);
+        }
+    };
+    // EARLY without a chain warp: warp 0 folds the partials after a barrier and publishes
+    auto early_publish = [&](uint32_t k) {
+        const uint64_t t64 = tile_of(k);
+        if (!tile_is_staged(t64) || t64 == 0)
+            return;
+        A v = lane < kScanWarps ? early_val[k % NS][lane] : ident;
+        v = WarpReduce<Op, A>::template run<32>(v);
+        if (lane == 0)
+            state.publish((uint32_t) t64, kAggregate, v);
+    };
+    if constexpr (EARLY) {
+        for (uint32_t k = 0; k + 1 < STAGES; ++k) {
+            early_reduce(k);
+            if constexpr (!CHAIN) {
+                scan_warps_sync();
+                if (warp == 0) early_publish(k);
+            }
+        }
+    }
+
+    // ===================================================================================
+    //  Scan warps
+    // ===================================================================================
+    for (uint32_t it = 0;; ++it) {
+        const uint64_t tile64 = tile_of(it);
+        if (tile64 >= p.tiles)
+            break;
+        const uint32_t tile = (uint32_t) tile64;
+        const uint32_t stage = it % NS;
+        const uint64_t tile_base = tile64 * TILE;   // scan-order position
+        const bool staged = tile_is_staged(tile64);
+
+        // ---- load + thread-local segmented scan ----------------------------------
+        A incl[ROWS][V];
+        uint32_t head_mask[ROWS];   // bit e: element e of the unit starts a segment
+        A unit_val[ROWS];           // aggregate after the last head of the unit
+
+        Vec16<T> raw[ROWS];
+        if constexpr (EARLY)
+            early_reduce(it + STAGES - 1);
+        if constexpr (STAGED) {
+            if (staged) {
+                mbar_wait(&full_bar[stage], (it / NS) & 1u);
+                const uint8_t *src = stage_mem + (size_t) stage * Geom::TILE_BYTES;
+                #pragma unroll
+                for (uint32_t k = 0; k < ROWS; ++k) {
+                    const uint32_t u = (warp * ROWS + k) * 32 + lane;
+                    const uint32_t off = rev ? Geom::TILE_BYTES - (u + 1) * 16 : u * 16;
+                    *reinterpret_cast<uint4 *>(&raw[k]) = lds128(src + off);
+                }
+            }
+            scan_warps_sync();                       // stage is free again
+            if (tid == kScanFetchTid)                // refill before the phases below
+                issue(stage, tile64 + (uint64_t) STAGES * gridDim.x);
+            if constexpr (EARLY && !CHAIN) {
+                if (warp == 0) early_publish(it + STAGES - 1);
+            }
+        }
+
+        #pragma unroll
+        for (uint32_t k = 0; k < ROWS; ++k) {
+            const uint64_t s0 = tile_base + (uint64_t) (((warp * ROWS + k) * 32 + lane) * V);
+            A x[V];
+            if (staged) {
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e)
+                    x[e] = to_acc<A>(rev ? raw[k].v[V - 1 - e] : raw[k].v[e]);
+            } else if (s0 >= size) {
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e) x[e] = ident;
+            } else if (VEC && s0 + V <= size) {
+                const T *src = rev ? in + (size - s0 - V) : in + s0;
+                Vec16<T> v = p.in_place ? ld_vec<T>(src) : ld_stream<T>(src);
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e)
+                    x[e] = to_acc<A>(rev ? v.v[V - 1 - e] : v.v[e]);
+            } else {
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e) {
+                    const uint64_t s = s0 + e;
+                    x[e] = s < size ? to_acc<A>(in[rev ? size - 1 - s : s]) : ident;
+                }
+            }
+
+            uint32_t hm = 0;
+            if constexpr (SEG) {
+                if (s0 < size) {
+                    // forward: head iff i % bs == 0; reverse: head iff (i + 1) % bs == 0, i = size-1-s
+                    uint32_t r = rev ? mod_bs((uint64_t) size - s0) : mod_bs(s0);
+                    #pragma unroll
+                    for (uint32_t e = 0; e < V; ++e) {
+                        hm |= (r == 0 ? 1u : 0u) << e;
+                        if (rev) r = r == 0 ? bs - 1 : r - 1;
+                        else     r = r + 1 == bs ? 0 : r + 1;
+                    }
+                }
+            }
+            head_mask[k] = hm;
+
+            A run = ident;
+            #pragma unroll
+            for (uint32_t e = 0; e < V; ++e) {
+                if (SEG && ((hm >> e) & 1u)) run = x[e];
+                else run = Op::template apply<A>(run, x[e]);
+                incl[k][e] = run;
+            }
+            unit_val[k] = run;
+        }
+
+        // ---- warp-level: scan the units of each row across lanes, chain the rows ---
+        A unit_prefix[ROWS];        // value entering the unit, from inside this warp
+        uint32_t unit_pflag = 0;    // bit k: a head precedes unit k inside this warp
+        A wcarry = ident;
+        bool wflag = false;
+        #pragma unroll
+        for (uint32_t k = 0; k < ROWS; ++k) {
+            uint32_t hb = 0, seg = 0;
+            if constexpr (SEG) {
+                hb = __ballot_sync(kFullMask, head_mask[k] != 0);
+                const uint32_t le = hb & lanemask_le();
+                seg = le ? 31u - __clz(le) : 0u;
+            }
+            A v = unit_val[k];
+            #pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const A t = shfl_up(v, d);
+                if (lane >= d + seg)
+                    v = Op::template apply<A>(t, v);
+            }
+            A ex = shfl_up(v, 1);
+            if (lane == 0) ex = ident;
+            const bool ef = SEG && (hb & lanemask_lt()) != 0;
+            unit_prefix[k] = ef ? ex : Op::template apply<A>(wcarry, ex);
+            if (wflag || ef) unit_pflag |= 1u << k;
+
+            const A row_val = shfl_idx(v, 31);
+            const bool row_flag = SEG && hb != 0;
+            wcarry = row_flag ? row_val : Op::template apply<A>(wcarry, row_val);
+            wflag = wflag || row_flag;
+        }
+        if (lane == 0) {
+            warp_val[warp] = wcarry;
+            warp_flag[warp] = wflag;
+        }
+        scan_warps_sync();
+
+        // ---- CTA-level: prefix over the preceding warps, tile aggregate -----------
+        A pv = ident, tv = ident;
+        bool pf = false, tf = false;
+        #pragma unroll
+        for (uint32_t w = 0; w < kScanWarps; ++w) {
+            const A wv = warp_val[w];
+            const bool wf = SEG && warp_flag[w];
+            if (w == warp) { pv = tv; pf = tf; }
+            tv = wf ? wv : Op::template apply<A>(tv, wv);
+            tf = tf || wf;
+        }
+
+        // ---- the tile's carry ----------------------------------------------------------
+        A tile_carry;
+        if constexpr (CHAIN) {
+            mbar_wait(&carry_bar[stage], (it / NS) & 1u);     // computed by the chain warp long ago
+            tile_carry = carry_ring[stage];
+        } else {
+            // decoupled look-back by warp 0 while the other warps wait
+            if (warp == 0) {
+                A excl = ident;
+                if (tile == 0) {
+                    if (p.carry_in) excl = to_acc<A>(*(const T *) p.carry_in);
+                    if (lane == 0)
+                        state.publish(0, kPrefix, tf ? tv : Op::template apply<A>(excl, tv));
+                } else if (p.debug & 1) {
+                    excl = ident;
+                } else {
+                    if (lane == 0 && tf)
+                        state.publish(tile, kPrefix, tv);      // complete: the segment starts inside
+                    else if (lane == 0 && !(EARLY && staged))      // (EARLY: published when the copy landed)
+                        state.publish(tile, kAggregate, tv);
+                    excl = scan_lookback<Op, A>(state, tile, lane);
+                    if (lane == 0 && !tf)
+                        state.publish(tile, kPrefix, Op::template apply<A>(excl, tv));
+                }
+                if (lane == 0)
+                    carry_smem = excl;
+            }
+            scan_warps_sync();
+            tile_carry = carry_smem;
+        }
+        if (p.total_out && tile == p.tiles - 1 && tid == 0)
+            *(T *) p.total_out = from_acc<T>(tf ? tv : Op::template apply<A>(tile_carry, tv));
+
+        // ---- combine and store -----------------------------------------------------
+        const A warp_in = pf ? pv : Op::template apply<A>(tile_carry, pv);
+        #pragma unroll
+        for (uint32_t k = 0; k < ROWS; ++k) {
+            const uint64_t s0 = tile_base + (uint64_t) (((warp * ROWS + k) * 32 + lane) * V);
+            if (s0 >= size)
+                continue;
+            const bool cut = (unit_pflag >> k) & 1u;
+            const A enter = cut ? unit_prefix[k] : Op::template apply<A>(warp_in, unit_prefix[k]);
+            const uint32_t hm = head_mask[k];
+
+            A res[V];
+            bool seen = false;
+            A prev = enter;                         // inclusive value of the previous element
+            #pragma unroll
+            for (uint32_t e = 0; e < V; ++e) {
+                const bool head = SEG && ((hm >> e) & 1u);
+                seen = seen || head;
+                const A inc = seen ? incl[k][e] : Op::template apply<A>(enter, incl[k][e]);
+                res[e] = p.exclusive ? (head ? ident : prev) : inc;
+                prev = inc;
+            }
+
+            if (VEC && s0 + V <= size) {
+                Vec16<T> v;
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e)
+                    v.v[rev ? V - 1 - e : e] = from_acc<T>(res[e]);
+                if ((p.debug & 2) && v.v[0] != T(12345))
+                    continue;
+                st_stream<T>(rev ? out + (size - s0 - V) : out + s0, v);
+            } else {
+                #pragma unroll
+                for (uint32_t e = 0; e < V; ++e) {
+                    const uint64_t s = s0 + e;
+                    if (s < size)
+                        out[rev ? size - 1 - s : s] = from_acc<T>(res[e]);
+                }
+            }
+        }
+    }
+}
+
+} // namespace djb

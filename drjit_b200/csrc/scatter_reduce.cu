@@ -72,8 +72,8 @@ __device__ __forceinline__ bool warp_combine(uint32_t active, uint32_t idx, T &v
     const uint32_t peers = __match_any_sync(active, idx);
     const uint32_t lane = lane_id();
     const bool leader = (peers & lanemask_lt()) == 0;
-    if (peers == (1u << lane))
-        return true;
+    // (no early exit for lanes without peers: every lane of `active` must reach the
+    // ballots / shuffles below)
     // walk the peer set: every lane pulls the values of its peers (leader's result is used)
     T acc = v;
     uint32_t rest = peers & ~(1u << lane);
