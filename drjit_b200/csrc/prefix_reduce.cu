@@ -35,7 +35,8 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
 
     static int occupancy = 0; // per instantiation
     if (occupancy == 0) {
-        if (smem > 48 * 1024)
+        // (static + dynamic shared memory together may exceed the 48 KiB default)
+        if (smem >= 32 * 1024)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         DJB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, threads, smem));
         if (occupancy < 1) occupancy = 1;

@@ -29,10 +29,12 @@ struct Error : std::runtime_error {
 #define DJB_CUDA_CHECK(expr)                                                             \
     do {                                                                                 \
         cudaError_t err__ = (expr);                                                      \
-        if (err__ != cudaSuccess)                                                        \
+        if (err__ != cudaSuccess) {                                                      \
+            (void) cudaGetLastError(); /* do not leak a launch error into the next call */ \
             ::djb::raise(DRJIT_B200_ECUDA, "cuda_check(): API error %04i (%s): \"%s\" in " \
                          "%s:%i.", (int) err__, cudaGetErrorName(err__),                 \
                          cudaGetErrorString(err__), __FILE__, __LINE__);                 \
+        }                                                                                \
     } while (0)
 
 struct DeviceProps {

@@ -17,8 +17,11 @@ from drjit_b200 import ReduceOp, VarType, ops  # noqa: E402
 PEAK = 6451.8
 
 
+WARM = 3
+
+
 def timeit(fn, reps):
-    for _ in range(3):
+    for _ in range(WARM):
         fn()
     torch.cuda.synchronize()
     ts = []
@@ -35,7 +38,10 @@ def main():
     ap.add_argument("prims", nargs="*", default=["all"])
     ap.add_argument("--log2", type=int, default=None)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
     a = ap.parse_args()
+    global WARM
+    WARM = a.warm
     want = set(a.prims)
     dev = "cuda"
 
