@@ -57,10 +57,15 @@ def measured_peaks():
 #  clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Polls nvidia-smi every 100 ms from before the warm-up until after the timed region. The
+    median SM clock is taken over the samples that fall inside the timed region; when that
+    region is shorter than a few polling periods, over warm-up + timed steps (same load), and
+    `window` says which."""
+
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.reasons = set()
+        self.samples = []       # (monotonic time, sm MHz, max MHz)
+        self.reasons = []       # (monotonic time, name)
         self.proc = None
 
     def start(self):
@@ -75,25 +80,56 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_first(self, timeout=10.0):
+        """nvidia-smi needs a second or so to start: block until it delivers"""
+        t0 = time.monotonic()
+        while self.proc and not self.samples and time.monotonic() - t0 < timeout:
+            time.sleep(0.05)
+
     def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
+            now = time.monotonic()
             try:
-                self.samples.append((float(parts[0]), float(parts[1])))
+                self.samples.append((now, float(parts[0]), float(parts[1])))
                 for n, v in zip(names, parts[2:6]):
                     if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                        self.reasons.append((now, n))
             except (ValueError, IndexError):
                 pass
 
-    def stop(self):
+    def stop(self, load_start=None, timed_start=None, timed_end=None):
         if self.proc:
             self.proc.terminate()
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "window": "nvidia-smi gave no samples"}
+        window = "timed steps"
+        sel = [s for s in self.samples if timed_start is not None and timed_start <= s[0] <= timed_end]
+        lo, hi = timed_start, timed_end
+        if len(sel) < 3 and load_start is not None:
+            window = "warm-up + timed steps (timed region shorter than 3 polling periods)"
+            sel = [s for s in self.samples if load_start <= s[0] <= timed_end]
+            lo = load_start
+        if not sel:
+            window, sel, lo, hi = "whole run", self.samples, self.samples[0][0], self.samples[-1][0]
+        sm = sorted(s[1] for s in sel)
+        reasons = sorted({n for t, n in self.reasons if lo <= t <= hi})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": sel[0][2], "reasons": reasons,
+                "samples": len(sel), "window": window}
+
+
+def measured_traffic(kernel, elements):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when the capture
+    was taken at another size."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f)[kernel]
+        return float(e["dram_bytes_per_launch"]) if int(e["elements"]) == int(elements) else None
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -289,25 +325,40 @@ def main():
             if events is not None:
                 events[i][1].record()
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    barrier()
+    t_load = time.monotonic()
+    # W warm-up steps, padded (same count on every rank) so that the clocks are sampled under
+    # this load for >= 0.5 s before the timed region starts
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    elapsed = time.monotonic() - t_load
+    extra = 0 if elapsed >= 0.5 else min(2000, int((0.5 - elapsed) / max(elapsed / args.warmup, 1e-4)) + 1)
+    if world > 1:
+        t = torch.tensor([extra], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extra = int(t.item())
+    for _ in range(extra):
+        one_step()
+    barrier()
     dr.launch_count(reset=True)
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prims]
           for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_timed0 = time.monotonic()
     start.record()
     for k in range(args.steps):
         one_step(ev[k])
     end.record()
     barrier()
+    t_timed1 = time.monotonic()
     launches = dr.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_load, t_timed0, t_timed1) if rank == 0 else None
 
     total_ms = start.elapsed_time(end)
     per_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps
@@ -343,7 +394,8 @@ def main():
     scan = primitives["prefix_sum_u32"]
     roofline = {"bound": "hbm", "kernel": "prefix_reduce_kernel<u32,Add> (exclusive prefix_sum, 2^30 elements per rank)",
                 "achieved": scan["GBps"] / world, "peak": peak, "unit": "GB/s",
-                "frac": round(scan["GBps"] / world / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(scan["GBps"] / world / peak, 4),
+                "traffic": measured_traffic("prefix_reduce_kernel", size["prefix_sum_u32"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": size["prefix_sum_u32"] * 8.0}
 
     cpu_baseline = None

@@ -4,23 +4,17 @@
  * Replaces CUDAThreadState::compress (ext/drjit-core/src/cuda_ts.cpp:683-763) and the kernels
  * compress_small / compress_large / compress_large_init (resources/compress.cuh:23-156).
  *
- * Design. Same single-pass skeleton as the scan (scan_kernel.cuh: ticketed persistent tiles,
- * TMA-staged input ring, decoupled look-back on packed 64-bit descriptors), specialised for
- * 1-byte flags:
- *  - a tile is 32 KiB of mask bytes (8 KiB for small masks), fetched by `cp.async.bulk` two
- *    tiles ahead; each thread turns its 8 x 16-byte units into 16-bit masks with three integer
- *    ops per word, so ranks come from popc instead of a 17-step scalar scan per thread
- *    (compress.cuh:101-109);
- *  - after the look-back every warp expands its rows (512 mask bytes each) into a private,
- *    bank-skewed 16-bit staging row and streams the indices out with fully coalesced stores --
- *    only __syncwarp() is needed; the reference issues scattered 4-byte stores straight to
- *    global memory behind 14 block-wide barriers (compress.cuh:112-154);
- *  - the mask is never written (the reference zero-pads the caller's buffer, cuda_ts.cpp:746-748);
- *    the ragged tail is bounds-checked instead;
- *  - the count goes to a device-mapped pinned word, one launch + one memset in total.
+ * Design: compress_kernel.cuh. Differences to the reference that are visible at the seam:
+ *  - the mask is never written (the reference zero-pads the caller's buffer up to the next
+ *    multiple of 2048, cuda_ts.cpp:746-748); the ragged tail is bounds-checked instead;
+ *  - the count goes to a device-mapped pinned word; one launch + one memset in total (the
+ *    reference: init kernel + main kernel + 14 block-wide barriers per 2048 mask bytes and
+ *    scattered 4-byte index stores straight to global memory, compress.cuh:112-154).
  */
 #include "compress_kernel.cuh"
 #include "runtime.h"
+
+#include <cstdlib>
 
 namespace djb {
 
@@ -45,7 +39,7 @@ static void launch_compress(cudaStream_t stream, CompressParams &p, Scratch &scr
     DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 
     // Cooperative launch: all CTAs co-resident (static tile schedule, see scan_kernel.cuh)
-    const uint32_t grid = std::min(p.tiles, dev.sm_count * (uint32_t) occupancy);
+    const uint32_t grid = std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kCompWindowLoads * kCompThreads);
     void *args[] = { (void *) &p };
     DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(kCompThreads), args, smem, stream));
     DJB_POST_LAUNCH();

@@ -1,6 +1,26 @@
 /*
- * compress_kernel.cuh -- device side of the mask compaction (see compress.cu for the design).
- * Host-side dispatch: compress.cu; geometry sweep: scripts/sweep_compress.cu.
+ * compress_kernel.cuh -- device side of the mask compaction (host side: compress.cu; geometry
+ * sweep: scripts/sweep_compress.cu).
+ *
+ * Single pass over the mask, static round-robin tile schedule on a cooperative grid, TMA ring
+ * for the input, windowed carry between tiles (same scheme as scan_kernel.cuh, "WINDOW").
+ * What keeps the kernel off the issue limit (the first version spent 1.05 warp instructions per
+ * mask byte, two thirds of them in a per-bit `while (m)` loop, skewed staging addresses and the
+ * copy-out: profiles/r1_ncu_full.md, profiles/r1_compress_lines.txt):
+ *   * a tile is decoded exactly once, one iteration ahead: the 16-bit masks of the next tile
+ *     live in ROWS/2 registers per thread, its warp counts in a 3-deep shared-memory ring. The
+ *     TMA stage is released right after that decode, so STAGES tiles are always in flight.
+ *   * the tile's count is published as soon as it is decoded; a tile's output offset is the
+ *     running sum of the counts of all earlier tiles, which every CTA advances by the G counts
+ *     between its previous and its current tile (one or two 8-byte L2 loads per thread, issued
+ *     before the decode of the next tile and consumed after it). No look-back, no chain between
+ *     CTAs, one __syncthreads per tile.
+ *   * per-row ranks come from one shuffle scan per PAIR of rows (two 16-bit counters per word).
+ *   * a thread expands its 16-bit mask without a data-dependent loop: two look-ups in a 256-entry
+ *     table (byte -> the positions of its set bits as packed nibbles) give a 64-bit nibble
+ *     stream; sixteen predicated 16-bit stores with immediate offsets put it into the warp's
+ *     staging row (no per-entry address arithmetic), from where the indices leave with fully
+ *     coalesced stores; only __syncwarp() is needed.
  */
 #pragma once
 
@@ -13,60 +33,83 @@ constexpr uint32_t kCompThreads = 256;
 constexpr uint32_t kCompWarps = kCompThreads / 32;
 constexpr uint32_t kCompUnit = 16;                                   // mask bytes per load
 constexpr uint32_t kCompFetchTid = kCompThreads - 32;                // issues the TMA copies
-constexpr uint32_t kCompLookbackLoads = 8;                           // look-back window = 256 tiles
 constexpr uint32_t kCompRowSlots = 32 * kCompUnit;                   // outputs of one warp row
-constexpr uint32_t kCompRowStride = kCompRowSlots + (kCompRowSlots >> 6) * 2 + 8;  // skewed, u16 entries
 
-enum : uint32_t { kCInvalid = 0, kCAggregate = 1, kCPrefix = 2 };
+enum : uint32_t { kCInvalid = 0, kCAggregate = 1 };
 
 struct CompressParams {
     const uint8_t *in;
     uint32_t *out;
-    uint64_t *state;      // tile descriptors {count << 32 | status}, zero on entry
+    uint64_t *state;      // tile descriptors {count << 32 | kCAggregate}, zero on entry
     uint32_t *count_out;  // device-accessible
     uint32_t size, tiles, index_base;
 };
 
-/// One bit per non-zero byte of a 32-bit word (bit k <- byte k)
-__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w) {
-    const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; // bit 7 of each non-zero byte
-    return (((nz >> 7) * 0x01020408u) >> 24) & 0xfu;
+constexpr uint32_t kCompWindowLoads = 3;                     // carry window: grids of up to 768 CTAs
+constexpr uint32_t kComp2RowStride = kCompRowSlots;          // u16 entries per warp staging row
+
+/// bit k <- (byte k of the 16-byte unit is non-zero)
+__device__ __forceinline__ uint32_t unit_mask16(const uint4 &v) {
+    auto top_nibble = [](uint32_t w) -> uint32_t {
+        const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; // bit 7 of each non-zero byte
+        return nz * 0x00204081u;        // bits 28..31 <- bytes 0..3 (no carries: all partial products are disjoint)
+    };
+    return (top_nibble(v.x) >> 28) | ((top_nibble(v.y) >> 24) & 0xf0u) |
+           ((top_nibble(v.z) >> 20) & 0xf00u) | ((top_nibble(v.w) >> 16) & 0xf000u);
 }
 
-/// Staging slot (16-bit entries) -> halfword index in shared memory. One padding word per
-/// 32 words keeps the runs written by different lanes on different banks even when every
-/// lane writes a full 16-entry run ("compress").
-__device__ __forceinline__ uint32_t skew(uint32_t slot) { return slot + ((slot >> 6) << 1); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((uint16_t) v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+/// (a & b) | c in one LOP3
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
-/// ROWS 16-byte units per thread: tile = 256 * ROWS * 16 mask bytes (ROWS = 8: 32768).
-/// STAGES > 0: 16-byte aligned masks, full tiles arrive through the TMA ring; STAGES == 0:
-/// direct loads (unaligned masks).
 template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS>
 __global__ void __launch_bounds__(kCompThreads, MIN_CTAS)
 compress_kernel(const CompressParams p) {
+    static_assert(ROWS % 2 == 0, "rows are ranked in pairs");
     constexpr uint32_t TILE = kCompThreads * ROWS * kCompUnit;
+    constexpr uint32_t PAIRS = ROWS / 2;
     constexpr bool STAGED = STAGES > 0;
-    constexpr bool EARLY = STAGES >= 2;     // early tile counts, see scan_kernel.cuh
+    constexpr uint32_t NS = STAGED ? STAGES : 1;
     static_assert(TILE <= 65536, "tile-local offsets are staged as 16-bit values");
     extern __shared__ __align__(128) uint8_t stage_mem[];       // STAGES x TILE
-    __shared__ uint16_t row_stage[kCompWarps][kCompRowStride];
-    __shared__ uint64_t full_bar[STAGED ? STAGES : 1];
-    __shared__ uint32_t warp_cnt[kCompWarps];
-    __shared__ uint32_t early_cnt[kCompWarps];
-    __shared__ uint32_t base_smem;
+    __shared__ __align__(16) uint16_t row_stage[kCompWarps][kComp2RowStride];
+    __shared__ uint32_t lut[256];           // byte -> positions of its set bits, one nibble each, ascending
+    __shared__ uint64_t full_bar[NS];
+    __shared__ uint32_t wcnt[4][kCompWarps];    // per-warp counts of tiles it-1 .. it+2
+    __shared__ uint32_t win_cnt[2][kCompWarps]; // per-warp partial sums of the carry window
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t size = p.size;
+    const bool aligned = (((uintptr_t) p.in) & 15u) == 0;
 
-    // static round-robin tile schedule + cooperative launch, see scan_kernel.cuh
+    {   // expansion table
+        uint32_t e = 0, n = 0;
+        #pragma unroll
+        for (uint32_t b = 0; b < 8; ++b)
+            if ((tid >> b) & 1u) { e |= b << (4 * n); ++n; }
+        lut[tid] = e;
+    }
+
     uint64_t policy = 0;
-    auto tile_is_staged = [&](uint32_t tile) -> bool {
-        return tile < p.tiles && (uint64_t) (tile + 1) * TILE <= size;
+    auto tile_of = [&](uint32_t k) -> uint64_t { return (uint64_t) blockIdx.x + (uint64_t) k * gridDim.x; };
+    auto tile_is_staged = [&](uint64_t tile) -> bool {
+        return STAGED && tile < p.tiles && (tile + 1) * TILE <= size;
     };
-    auto issue = [&](uint32_t s, uint32_t tile) {
+    auto issue = [&](uint32_t s, uint64_t tile) {
         if (tile_is_staged(tile)) {
             mbar_expect_tx(&full_bar[s], TILE);
-            bulk_load(stage_mem + (size_t) s * TILE, p.in + (uint64_t) tile * TILE, TILE, &full_bar[s], policy);
+            bulk_load(stage_mem + (size_t) s * TILE, p.in + tile * TILE, TILE, &full_bar[s], policy);
         }
     };
     if constexpr (STAGED) {
@@ -76,94 +119,38 @@ compress_kernel(const CompressParams p) {
             fence_proxy_async();
             policy = policy_evict_first();
             #pragma unroll
-            for (uint32_t s = 0; s < STAGES; ++s) issue(s, blockIdx.x + s * gridDim.x);
+            for (uint32_t s = 0; s < STAGES; ++s) issue(s, tile_of(s));
         }
-        __syncthreads();
     }
+    __syncthreads();
 
-    // EARLY: count the k-th tile of this CTA straight from its stage as soon as it has landed
-    // and publish the count STAGES-1 iterations before the tile itself is compacted
-    auto early_count = [&](uint32_t k) -> bool {
-        const uint64_t t64 = (uint64_t) blockIdx.x + (uint64_t) k * gridDim.x;
-        if (t64 >= p.tiles || !tile_is_staged((uint32_t) t64))
-            return false;
-        constexpr uint32_t NS = STAGED ? STAGES : 1;
-        const uint32_t s = k % NS;
-        mbar_wait(&full_bar[s], (k / NS) & 1u);
-        const uint8_t *src = stage_mem + (size_t) s * TILE;
-        uint32_t c = 0;
+    // Masks of this CTA's k-th tile -> mk (two 16-bit masks per word); the warp's count goes
+    // to the ring. Rows past the end of the array decode as empty.
+    auto decode = [&](uint32_t k, uint32_t (&mk)[PAIRS]) {
+        const uint64_t tile64 = tile_of(k);
         #pragma unroll
-        for (uint32_t r = 0; r < ROWS; ++r) {
-            const uint4 v = lds128(src + ((warp * ROWS + r) * 32 + lane) * kCompUnit);
-            c += __popc(nonzero_nibble(v.x) | (nonzero_nibble(v.y) << 4) |
-                        (nonzero_nibble(v.z) << 8) | (nonzero_nibble(v.w) << 12));
-        }
-        c = __reduce_add_sync(kFullMask, c);
-        if (lane == 0) early_cnt[warp] = c;
-        return true;
-    };
-    auto early_publish = [&](uint32_t k) {
-        uint32_t c = lane < kCompWarps ? early_cnt[lane] : 0u;
-        c = __reduce_add_sync(kFullMask, c);
-        const uint32_t t = blockIdx.x + k * gridDim.x;
-        if (lane == 0 && t != 0)
-            st_relaxed_u64(p.state + t, ((uint64_t) c << 32) | kCAggregate);
-    };
-    if constexpr (EARLY) {
-        for (uint32_t k = 0; k + 1 < STAGES; ++k) {
-            const bool did = early_count(k);
-            __syncthreads();
-            if (warp == 0 && did) early_publish(k);
-            __syncthreads();
-        }
-    }
-
-    for (uint32_t it = 0;; ++it) {
-        const uint64_t tile64 = (uint64_t) blockIdx.x + (uint64_t) it * gridDim.x;
+        for (uint32_t i = 0; i < PAIRS; ++i) mk[i] = 0;
         if (tile64 >= p.tiles)
-            break;
-        const uint32_t tile = (uint32_t) tile64;
-        const uint32_t stage = STAGED ? it % STAGES : 0;
-        const uint64_t tile_base = (uint64_t) tile * TILE;
-        const bool staged = STAGED && tile_is_staged(tile);
-
-        // ---- load, byte flags -> bit masks ------------------------------------------
-        uint32_t mask[ROWS];
-        bool early_done = false;
-        if constexpr (EARLY)
-            early_done = early_count(it + STAGES - 1);
-        if constexpr (STAGED) {
-            if (staged) {
-                mbar_wait(&full_bar[stage], (it / STAGES) & 1u);
-                const uint8_t *src = stage_mem + (size_t) stage * TILE;
-                #pragma unroll
-                for (uint32_t k = 0; k < ROWS; ++k) {
-                    const uint4 v = lds128(src + ((warp * ROWS + k) * 32 + lane) * kCompUnit);
-                    mask[k] = nonzero_nibble(v.x) | (nonzero_nibble(v.y) << 4) |
-                              (nonzero_nibble(v.z) << 8) | (nonzero_nibble(v.w) << 12);
-                }
-            }
-            __syncthreads();                         // stage is free again
-            if (tid == kCompFetchTid) {
-                const uint64_t next = tile64 + (uint64_t) STAGES * gridDim.x;
-                if (next < p.tiles) issue(stage, (uint32_t) next);
-            }
-            if constexpr (EARLY) {
-                if (warp == 0 && early_done) early_publish(it + STAGES - 1);
-            }
-        }
-        if (!staged) {
-            const bool aligned = (((uintptr_t) p.in) & 15u) == 0;
+            return;
+        if (tile_is_staged(tile64)) {
+            const uint32_t s = k % NS;
+            mbar_wait(&full_bar[s], (k / NS) & 1u);
+            const uint8_t *src = stage_mem + (size_t) s * TILE;
             #pragma unroll
-            for (uint32_t k = 0; k < ROWS; ++k) {
-                const uint64_t s0 = tile_base + (uint64_t) (((warp * ROWS + k) * 32 + lane) * kCompUnit);
+            for (uint32_t r = 0; r < ROWS; ++r) {
+                const uint4 v = lds128(src + ((warp * ROWS + r) * 32 + lane) * kCompUnit);
+                mk[r / 2] |= unit_mask16(v) << (16 * (r & 1u));
+            }
+        } else {
+            const uint64_t tile_base = tile64 * TILE;
+            #pragma unroll
+            for (uint32_t r = 0; r < ROWS; ++r) {
+                const uint64_t s0 = tile_base + (uint64_t) (((warp * ROWS + r) * 32 + lane) * kCompUnit);
                 uint32_t m = 0;
                 if (s0 < size) {
                     if (aligned && s0 + kCompUnit <= size) {
                         const Vec16<uint32_t> v = ld_stream<uint32_t>(p.in + s0);
-                        #pragma unroll
-                        for (uint32_t j = 0; j < 4; ++j)
-                            m |= nonzero_nibble(v.v[j]) << (4 * j);
+                        m = unit_mask16(*reinterpret_cast<const uint4 *>(&v));
                     } else {
                         #pragma unroll
                         for (uint32_t e = 0; e < kCompUnit; ++e)
@@ -171,106 +158,150 @@ compress_kernel(const CompressParams p) {
                                 m |= 1u << e;
                     }
                 }
-                mask[k] = m;
+                mk[r / 2] |= m << (16 * (r & 1u));
             }
         }
-
-        // ---- ranks inside the warp (warp-contiguous item order: row-major, then lane) ------
-        uint32_t rank[ROWS], row_total[ROWS], wtotal = 0;
+        uint32_t c = 0;
         #pragma unroll
-        for (uint32_t k = 0; k < ROWS; ++k) {
-            const uint32_t c = __popc(mask[k]);
-            uint32_t v = c;
+        for (uint32_t i = 0; i < PAIRS; ++i) c += __popc(mk[i]);
+        c = __reduce_add_sync(kFullMask, c);
+        if (lane == 0) wcnt[k % 4][warp] = c;
+    };
+    // warp 0, after the barrier that follows decode(k): the tile's count becomes visible to
+    // the look-backs of other CTAs one whole iteration before the tile itself is compacted
+    auto publish_aggregate = [&](uint32_t k) {
+        const uint64_t t = tile_of(k);
+        if (t >= p.tiles)
+            return;
+        uint32_t c = lane < kCompWarps ? wcnt[k % 4][lane] : 0u;
+        c = __reduce_add_sync(kFullMask, c);
+        if (lane == 0)
+            st_relaxed_u64(p.state + t, ((uint64_t) c << 32) | kCAggregate);
+    };
+
+    // Tiles are decoded (and their counts published) two iterations before they are compacted:
+    // with one iteration of slack the carry windows below were found polling for a fifth of all
+    // issued instructions (profiles/r1c), with two they find everything in place.
+    uint32_t cur[PAIRS], nxt[PAIRS], nxt2[PAIRS];
+    uint32_t carry = 0;                 // selected entries in all tiles before the current one
+    decode(0, cur);
+    __syncthreads();                                    // stage 0 is free, counts visible
+    if constexpr (STAGED) {
+        if (tid == kCompFetchTid) issue(0, tile_of(NS));
+    }
+    decode(1, nxt);
+    __syncthreads();
+    if constexpr (STAGED) {
+        if (tid == kCompFetchTid) issue(1 % NS, tile_of(1 + NS));
+    }
+    if (warp == 0) { publish_aggregate(0); publish_aggregate(1); }
+
+    const uint32_t lane16 = lane * kCompUnit;
+    const uint32_t stg_addr = smem_addr(row_stage[warp]);
+
+    for (uint32_t it = 0;; ++it) {
+        const uint64_t tile64 = tile_of(it);
+        if (tile64 >= p.tiles)
+            break;
+        const uint32_t tile = (uint32_t) tile64;
+
+        // ---- carry window: counts of the tiles between this CTA's previous tile and this one ----
+        // (scan_kernel.cuh, "WINDOW")
+        uint64_t wd[kCompWindowLoads];
+        const uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x, win_n = tile - win_lo;
+        #pragma unroll
+        for (uint32_t j = 0; j < kCompWindowLoads; ++j) {
+            const uint32_t o = j * kCompThreads + tid;
+            wd[j] = o < win_n ? ld_relaxed_u64(p.state + win_lo + o) : (uint64_t) kCAggregate;
+        }
+        // ---- decode the tile after the next one ----------------------------------------------
+        decode(it + 2, nxt2);
+        {
+            uint32_t w = 0;
+            #pragma unroll
+            for (uint32_t j = 0; j < kCompWindowLoads; ++j) {
+                while ((uint32_t) wd[j] == kCInvalid) {     // a CTA that runs behind: poll
+                    __nanosleep(20);
+                    wd[j] = ld_relaxed_u64(p.state + win_lo + j * kCompThreads + tid);
+                }
+                w += (uint32_t) (wd[j] >> 32);
+            }
+            w = __reduce_add_sync(kFullMask, w);
+            if (lane == 0) win_cnt[it & 1u][warp] = w;
+        }
+        __syncthreads();            // window sums, counts of tile it+2, stage of tile it+2 free
+        if constexpr (STAGED) {
+            if (tid == kCompFetchTid) issue((it + 2) % NS, tile_of(it + 2 + STAGES));
+        }
+        if (warp == 0) publish_aggregate(it + 2);
+        #pragma unroll
+        for (uint32_t w = 0; w < kCompWarps; ++w)
+            carry += win_cnt[it & 1u][w];
+        if (tile == p.tiles - 1 && tid == 0) {
+            uint32_t ttotal = 0;
+            #pragma unroll
+            for (uint32_t w = 0; w < kCompWarps; ++w) ttotal += wcnt[it % 4][w];
+            *p.count_out = carry + ttotal;
+        }
+
+        // ---- compaction of tile `it` -----------------------------------------------------------
+        uint32_t wprefix = 0;
+        #pragma unroll
+        for (uint32_t w = 0; w < kCompWarps; ++w)
+            if (w < warp) wprefix += wcnt[it % 4][w];
+        uint32_t *dst = p.out + carry + wprefix;
+        const uint32_t idx_warp = p.index_base + (uint32_t) (tile64 * TILE) + warp * ROWS * kCompRowSlots;
+
+        #pragma unroll
+        for (uint32_t i = 0; i < PAIRS; ++i) {
+            // ranks of two rows at once: 16-bit counters (a row selects at most 512 entries)
+            const uint32_t c2 = __popc(cur[i] & 0xffffu) | (__popc(cur[i] >> 16) << 16);
+            uint32_t v = c2;
             #pragma unroll
             for (uint32_t d = 1; d < 32; d <<= 1) {
                 const uint32_t t = shfl_up(v, d);
                 if (lane >= d) v += t;
             }
-            rank[k] = v - c;                      // exclusive, inside the row
-            row_total[k] = shfl_idx(v, 31);
-            wtotal += row_total[k];
-        }
-        if (lane == 0)
-            warp_cnt[warp] = wtotal;
-        __syncthreads();
-
-        uint32_t wprefix = 0, ttotal = 0;
-        #pragma unroll
-        for (uint32_t w = 0; w < kCompWarps; ++w) {
-            if (w == warp) wprefix = ttotal;
-            ttotal += warp_cnt[w];
-        }
-
-        // ---- look-back for the tile's first output slot (warp 0) -----------------------
-        if (warp == 0) {
-            uint32_t excl = 0;
-            if (tile == 0) {
-                if (lane == 0)
-                    st_relaxed_u64(p.state, ((uint64_t) ttotal << 32) | kCPrefix);
-            } else {
-                if (lane == 0 && !(EARLY && staged))
-                    st_relaxed_u64(p.state + tile, ((uint64_t) ttotal << 32) | kCAggregate);
-                int32_t pred = (int32_t) tile - 1 - (int32_t) lane;
-                auto consume = [&](int32_t first, uint64_t w) -> bool {
-                    while (__any_sync(kFullMask, (uint32_t) w == kCInvalid)) {
-                        __nanosleep(20);
-                        if (first >= 0) w = ld_relaxed_u64(p.state + first);
-                    }
-                    const uint32_t done = __ballot_sync(kFullMask, (uint32_t) w == kCPrefix);
-                    const uint32_t stop = done ? (uint32_t) __ffs(done) - 1 : 31u;
-                    excl += __reduce_add_sync(kFullMask, lane <= stop ? (uint32_t) (w >> 32) : 0u);
-                    return done != 0;
-                };
-                while (true) {
-                    // 8 windows of 32 descriptors per round, all loads in flight together; lanes
-                    // past the array start behave like a finished tile with count 0
-                    uint64_t w[kCompLookbackLoads];
+            const uint32_t tot2 = shfl_idx(v, 31), ex2 = v - c2;
+            #pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t m = (cur[i] >> (16 * h)) & 0xffffu;
+                const uint32_t c = (c2 >> (16 * h)) & 0xffffu, r = (ex2 >> (16 * h)) & 0xffffu,
+                               n = (tot2 >> (16 * h)) & 0xffffu;
+                // 64-bit nibble stream: positions of the set bits of m, ascending
+                const uint32_t lo = lut[m & 0xffu], hi = lut[m >> 8] + 0x88888888u;
+                const uint64_t q = (uint64_t) lo | ((uint64_t) hi << (4 * __popc(m & 0xffu)));
+                const uint32_t wa = stg_addr + 2 * r;
+                if (n > 64) {
                     #pragma unroll
-                    for (uint32_t j = 0; j < kCompLookbackLoads; ++j) {
-                        const int32_t idx = pred - 32 * (int32_t) j;
-                        w[j] = idx >= 0 ? ld_relaxed_u64(p.state + idx) : (uint64_t) kCPrefix;
-                    }
-                    bool found = false;
-                    #pragma unroll
-                    for (uint32_t j = 0; j < kCompLookbackLoads; ++j) {
-                        if (!found && consume(pred - 32 * (int32_t) j, w[j]))
-                            found = true;
-                    }
-                    if (found) break;
-                    pred -= 32 * (int32_t) kCompLookbackLoads;
+                    for (uint32_t j = 0; j < kCompUnit; ++j)
+                        if (j < c)
+                            sts_u16(wa + 2 * j, and_or((uint32_t) (q >> (4 * j)), 15u, lane16));
+                } else {
+                    // sparse row (n is warp-uniform): only as many rounds as the fullest lane needs
+                    const uint32_t cmax = __reduce_max_sync(kFullMask, c);
+                    uint64_t qq = q;
+                    for (uint32_t j = 0; j < cmax; ++j, qq >>= 4)
+                        if (j < c)
+                            sts_u16(wa + 2 * j, and_or((uint32_t) qq, 15u, lane16));
                 }
-                if (lane == 0)
-                    st_relaxed_u64(p.state + tile, ((uint64_t) (excl + ttotal) << 32) | kCPrefix);
-            }
-            if (lane == 0) {
-                base_smem = excl;
-                if (tile == p.tiles - 1)
-                    *p.count_out = excl + ttotal;
+                __syncwarp();
+                // coalesced copy-out, 128 slots per round
+                const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
+                for (uint32_t s0 = 0; s0 < n; s0 += 128) {
+                    #pragma unroll
+                    for (uint32_t t = 0; t < 4; ++t) {
+                        const uint32_t s = s0 + t * 32 + lane;
+                        if (s < n)
+                            dst[s] = idx_row + lds_u16(stg_addr + 2 * s);
+                    }
+                }
+                __syncwarp();
+                dst += n;
             }
         }
-        __syncthreads();
-
-        // ---- per warp: expand each row into the private staging row, stream it out ----------
-        uint32_t *dst = p.out + base_smem + wprefix;
-        const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        uint16_t *stg = row_stage[warp];
         #pragma unroll
-        for (uint32_t k = 0; k < ROWS; ++k) {
-            const uint32_t local0 = ((warp * ROWS + k) * 32 + lane) * kCompUnit;
-            uint32_t m = mask[k], r = rank[k];
-            while (m) {
-                const uint32_t b = (uint32_t) __ffs(m) - 1;
-                m &= m - 1;
-                stg[skew(r)] = (uint16_t) (local0 + b);
-                ++r;
-            }
-            __syncwarp();
-            const uint32_t n = row_total[k];
-            for (uint32_t s = lane; s < n; s += 32)
-                dst[s] = idx0 + stg[skew(s)];
-            __syncwarp();
-            dst += n;
-        }
+        for (uint32_t i = 0; i < PAIRS; ++i) { cur[i] = nxt[i]; nxt[i] = nxt2[i]; }
     }
 }
 

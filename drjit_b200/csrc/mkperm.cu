@@ -42,6 +42,7 @@ struct MkpermParams {
     uint32_t size, block_size, bucket_count;
     uint32_t n_groups, ctas_per_group, rows_per_group, row_elems; // row = slice of a group
     uint32_t index_base;
+    uint32_t row_stride;     // elements between histogram rows (0: bucket_count)
     uint8_t vec;
 };
 
@@ -139,7 +140,7 @@ mkperm_column_scan_kernel(const MkpermParams p, uint32_t tiles_per_group) {
     const bool valid = b < p.bucket_count;
     const uint32_t R = p.rows_per_group, seg = (R + 7) / 8,
                    r0 = min(warp * seg, R), r1 = min(r0 + seg, R);
-    const size_t B = p.bucket_count;
+    const size_t B = p.row_stride ? p.row_stride : p.bucket_count;   // elements between rows
     uint32_t *col = p.rows + (size_t) group * R * B + b;
 
     uint32_t sum = 0;
@@ -178,7 +179,7 @@ mkperm_column_scan_kernel(const MkpermParams p, uint32_t tiles_per_group) {
         running += t;
     }
     if (warp == 0)
-        p.totals[(size_t) group * B + b] = total;
+        p.totals[(size_t) group * p.bucket_count + b] = total;
 }
 
 // ---------------------------------------------------------------------------
@@ -335,160 +336,212 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
 //  The row-per-warp design above keeps one write cursor per (warp, bucket): with 4096 buckets
 //  and ~1900 rows that is 7.9 M cursors advancing 4 bytes at a time, the partially written
 //  sectors do not survive in L2 and every 4-byte store costs a 32-byte DRAM read-modify-write
-//  (measured: 1.93 GB written + 1.96 GB read for a 268 MB permutation, profiles/r1a). Here the
-//  array is cut into tiles of 16 Ki keys that all CTAs walk in the same order, so that at any
-//  time the whole chip writes into a narrow moving window of every bucket (a few KiB) that L2
-//  merges into full lines:
-//    K1 tile histogram : CTA c counts a contiguous chunk of tiles in shared memory (8.6 shared
-//                        atomics/clk/SM measured); before each tile it snapshots the running
-//                        counts -> tile_off[tile][bucket] (exclusive prefix inside the chunk).
-//    K2 column scan over the C chunk totals + bucket scan (kernels above).
-//    K3 tile scatter   : per tile: rank = shared atomicAdd (one per key), exclusive scan of the
-//                        tile histogram, keys re-ordered by bucket in shared memory, then
-//                        written out as runs: consecutive threads store consecutive entries.
+//  (measured: 1.93 GB written + 1.96 GB read for a 268 MB permutation). Here the array is cut
+//  into tiles that all CTAs walk in the same order, so that at any time the whole chip writes
+//  into a narrow moving window of every bucket (a few KiB) that L2 merges into full lines:
+//    K1 tile histogram : CTA c counts a contiguous chunk of tiles in shared memory (8.2 shared
+//                        atomics/clk/SM measured); per tile it records the running counts
+//                        before the tile (tile_off, exclusive prefix inside the chunk) and
+//                        the tile's own counts (cnt16).
+//    K2 column scan over the chunk totals + bucket scan (kernels above) + one tiny pass that
+//       folds the bucket starts into the chunk offsets.
+//    K3 tile scatter   : per tile: (1) bins: exclusive scan of the tile's counts -> one write
+//                        cursor per bucket in shared memory, plus the distance between a slot of
+//                        the tile-local order and its final position (all 128-bit loads/stores,
+//                        issued while the keys are still in flight); (2) keys: slot = shared
+//                        atomicAdd on the cursor, entry (bucket, local index) stored at the slot:
+//                        two shared-memory operations per key; (3) slots are copied out in order:
+//                        runs of equal buckets are contiguous in shared memory and in `perm`, so
+//                        consecutive threads store consecutive entries.
+//  The kernel is bound by the LSU pipe -- shared-memory wavefronts plus the sectors of the run-wise
+//  global stores (profiles/r1b: 11.5 sectors per store request at 16 Ki keys per tile and 4096
+//  buckets) -- which is why tiles are as large as shared memory allows: runs get longer.
 //  Ranks come from atomics, so the order inside a bucket is not the input order (same contract
 //  as the reference's "small"/"large" variants, jit.h:2404-2406); bucket boundaries, the offsets
 //  table and per-bucket contents are exact.
-constexpr uint32_t kTileThreads = 512;
-constexpr uint32_t kTileKeys = 16384;                      // keys per tile (ranks fit 16 bits)
-constexpr uint32_t kTileKeysPerThread = kTileKeys / kTileThreads;
+constexpr uint32_t kTileKeysPerThread = 32;
 constexpr uint32_t kTileMaxBuckets = 8192;
 
 struct MkpermTileParams {
     const uint32_t *values;
     uint32_t *perm;
-    uint32_t *tile_off;      // [tiles][buckets] exclusive prefix of the tile inside its chunk
-    uint32_t *rows;          // [chunks][buckets] chunk totals -> (column scan) exclusive chunk offsets
+    uint32_t *tile_off;      // [tiles][stride] exclusive prefix of the tile inside its chunk
+    uint16_t *tile_cnt;      // [tiles][stride] counts of the tile
+    uint32_t *rows;          // [chunks][stride] chunk totals -> exclusive chunk offsets (+ bucket starts)
     const uint32_t *bucket_start; // [buckets] after the bucket scan
-    uint32_t size, bucket_count, tiles, tiles_per_chunk, index_base;
+    uint32_t size, bucket_count, stride, tiles, tiles_per_chunk, index_base;
     uint8_t vec;
 };
 
 /// Loads the keys of one tile into registers (clamped to the last bucket: out-of-range keys are
 /// undefined behaviour in the reference; here they can at least not corrupt shared memory).
 /// local index of key (k, e): VEC: ((k * threads + tid) * 4 + e), else k * threads + tid.
+template <uint32_t THREADS>
 __device__ __forceinline__ void tile_load_keys(const MkpermTileParams &p, uint64_t tile_base, uint32_t n_tile,
                                                uint32_t (&key)[kTileKeysPerThread]) {
     const uint32_t tid = threadIdx.x, last = p.bucket_count - 1;
-    if (p.vec && n_tile == kTileKeys) {
+    if (p.vec && n_tile == THREADS * kTileKeysPerThread) {
         const uint4 *v = reinterpret_cast<const uint4 *>(p.values + tile_base);
         #pragma unroll
         for (uint32_t k = 0; k < kTileKeysPerThread / 4; ++k) {
-            const Vec16<uint32_t> t = ld_stream<uint32_t>(v + k * kTileThreads + tid);
+            const Vec16<uint32_t> t = ld_stream<uint32_t>(v + k * THREADS + tid);
             #pragma unroll
             for (uint32_t e = 0; e < 4; ++e) key[k * 4 + e] = min(t.v[e], last);
         }
     } else {
         #pragma unroll
         for (uint32_t k = 0; k < kTileKeysPerThread; ++k) {
-            const uint32_t i = k * kTileThreads + tid;
+            const uint32_t i = k * THREADS + tid;
             key[k] = i < n_tile ? min(__ldg(p.values + tile_base + i), last) : 0xffffffffu;
         }
     }
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_hist_kernel(const MkpermTileParams p) {
-    extern __shared__ uint32_t smem[];
+    constexpr uint32_t TILE = THREADS * kTileKeysPerThread;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t S = p.stride;
     uint32_t *hist = smem;                                  // running counts of this chunk
-    const uint32_t tid = threadIdx.x, B = p.bucket_count;
-    for (uint32_t b = tid; b < B; b += kTileThreads) hist[b] = 0;
+    uint32_t *prev = smem + S;                              // ... as of the previous tile
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t b = tid; b < S; b += THREADS) { hist[b] = 0; prev[b] = 0; }
 
     const uint32_t first = blockIdx.x * p.tiles_per_chunk,
                    end = min(first + p.tiles_per_chunk, p.tiles);
+    // snapshot before tile `tile` (tile == end: only the counts of the last tile are due)
+    auto snapshot = [&](uint32_t tile) {
+        for (uint32_t b = tid * 4; b < S; b += THREADS * 4) {
+            const uint4 h = *reinterpret_cast<const uint4 *>(hist + b);
+            const uint4 q = *reinterpret_cast<const uint4 *>(prev + b);
+            if (tile < end)
+                *reinterpret_cast<uint4 *>(p.tile_off + (size_t) tile * S + b) = h;
+            if (tile > first) {
+                const uint2 c = make_uint2((h.x - q.x) | ((h.y - q.y) << 16), (h.z - q.z) | ((h.w - q.w) << 16));
+                *reinterpret_cast<uint2 *>(p.tile_cnt + (size_t) (tile - 1) * S + b) = c;
+            }
+            *reinterpret_cast<uint4 *>(prev + b) = h;
+        }
+    };
     for (uint32_t tile = first; tile < end; ++tile) {
-        const uint64_t tile_base = (uint64_t) tile * kTileKeys;
-        const uint32_t n_tile = (uint32_t) min((uint64_t) kTileKeys, (uint64_t) p.size - tile_base);
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
         uint32_t key[kTileKeysPerThread];
-        tile_load_keys(p, tile_base, n_tile, key);          // loads in flight across the barrier
+        tile_load_keys<THREADS>(p, tile_base, n_tile, key);      // loads in flight across the barrier
         __syncthreads();                                    // previous tile's atomics are done
-        uint32_t *dst = p.tile_off + (size_t) tile * B;
-        for (uint32_t b = tid; b < B; b += kTileThreads) dst[b] = hist[b];
+        snapshot(tile);
         __syncthreads();
         #pragma unroll
         for (uint32_t k = 0; k < kTileKeysPerThread; ++k)
             if (key[k] != 0xffffffffu) atomicAdd(hist + key[k], 1u);
     }
     __syncthreads();
-    uint32_t *row = p.rows + (size_t) blockIdx.x * B;
-    for (uint32_t b = tid; b < B; b += kTileThreads) row[b] = hist[b];
+    snapshot(end);
+    uint32_t *row = p.rows + (size_t) blockIdx.x * S;
+    for (uint32_t b = tid; b < S; b += THREADS) row[b] = hist[b];
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2)
+/// rows[c][b] += bucket_start[b]: after this, rows[c][b] + tile_off[t][b] is the final position
+/// of the first key of bucket b in tile t (t in chunk c)
+__global__ void mkperm_fold_starts_kernel(uint32_t *rows, const uint32_t *bucket_start, uint32_t chunks,
+                                          uint32_t buckets, uint32_t stride) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= buckets) return;
+    const uint32_t s = bucket_start[b];
+    for (uint32_t c = blockIdx.y; c < chunks; c += gridDim.y)
+        rows[(size_t) c * stride + b] += s;
+}
+
+template <uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_scatter_kernel(const MkpermTileParams p) {
-    extern __shared__ uint32_t smem[];
-    const uint32_t B = p.bucket_count;
-    uint32_t *hist = smem;               // [B] tile counts -> exclusive tile-local starts
-    uint32_t *delta = smem + B;          // [B] global position of the bucket's run minus its local start
-    uint32_t *sorted = smem + 2 * B;     // [kTileKeys] (bucket << 16 | local index), ordered by bucket
-    __shared__ uint32_t warp_sum[kTileThreads / 32];
+    constexpr uint32_t TILE = THREADS * kTileKeysPerThread, WARPS = THREADS / 32;
+    static_assert(TILE <= 65536, "local indices are packed into 16 bits");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t S = p.stride;
+    uint32_t *cursor = smem;             // [S] next free slot of the bucket in the tile-local order
+    uint32_t *delta = smem + S;          // [S] final position of the bucket's run minus its local start
+    uint32_t *sorted = smem + 2 * S;     // [TILE] (bucket << 16 | local index), ordered by bucket
+    __shared__ uint32_t warp_sum[WARPS];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t per_thread = (B + kTileThreads - 1) / kTileThreads;    // bins per thread (contiguous)
 
     for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        const uint64_t tile_base = (uint64_t) tile * kTileKeys;
-        const uint32_t n_tile = (uint32_t) min((uint64_t) kTileKeys, (uint64_t) p.size - tile_base);
-        const bool vec = p.vec && n_tile == kTileKeys;
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
+        const bool vec = p.vec && n_tile == TILE;
 
         uint32_t key[kTileKeysPerThread];
-        tile_load_keys(p, tile_base, n_tile, key);
-        for (uint32_t b = tid; b < B; b += kTileThreads) hist[b] = 0;
-        __syncthreads();
+        tile_load_keys<THREADS>(p, tile_base, n_tile, key);     // in flight during the bin phase
 
-        // rank inside (tile, bucket): one shared-memory atomic per key
-        #pragma unroll
-        for (uint32_t k = 0; k < kTileKeysPerThread; ++k)
-            if (key[k] != 0xffffffffu)
-                key[k] = (key[k] << 16) | atomicAdd(hist + key[k], 1u);
-        __syncthreads();
-
-        // exclusive scan of the tile histogram; thread t owns bins [t * per_thread, ...)
+        // ---- (1) bins: thread t owns 8 consecutive buckets per round ----------------------
         {
-            const uint32_t b0 = tid * per_thread;
-            uint32_t sum = 0;
-            for (uint32_t j = 0; j < per_thread; ++j)
-                if (b0 + j < B) sum += hist[b0 + j];
-            uint32_t incl = sum;
-            #pragma unroll
-            for (uint32_t d = 1; d < 32; d <<= 1) {
-                const uint32_t t = shfl_up(incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane == 31) warp_sum[warp] = incl;
-            __syncthreads();
-            uint32_t wbase = 0;
-            #pragma unroll
-            for (uint32_t w = 0; w < kTileThreads / 32; ++w)
-                if (w < warp) wbase += warp_sum[w];
-            uint32_t run = wbase + incl - sum;
             const uint32_t chunk = tile / p.tiles_per_chunk;
-            const uint32_t *toff = p.tile_off + (size_t) tile * B, *crow = p.rows + (size_t) chunk * B;
-            for (uint32_t j = 0; j < per_thread; ++j) {
-                const uint32_t b = b0 + j;
-                if (b < B) {
-                    const uint32_t c = hist[b];
-                    hist[b] = run;
-                    delta[b] = p.bucket_start[b] + crow[b] + toff[b] - run;
-                    run += c;
+            const uint16_t *cnt = p.tile_cnt + (size_t) tile * S;
+            const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < S; base += THREADS * 8) {
+                const uint32_t b0 = base + tid * 8;
+                uint32_t c[8], g[8];
+                #pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) { c[j] = 0; g[j] = 0; }
+                if (b0 < S) {
+                    const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(cnt + b0));
+                    const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(toff + b0)),
+                                t1 = __ldg(reinterpret_cast<const uint4 *>(toff + b0 + 4)),
+                                r0 = __ldg(reinterpret_cast<const uint4 *>(crow + b0)),
+                                r1 = __ldg(reinterpret_cast<const uint4 *>(crow + b0 + 4));
+                    c[0] = cc.x & 0xffffu; c[1] = cc.x >> 16; c[2] = cc.y & 0xffffu; c[3] = cc.y >> 16;
+                    c[4] = cc.z & 0xffffu; c[5] = cc.z >> 16; c[6] = cc.w & 0xffffu; c[7] = cc.w >> 16;
+                    g[0] = t0.x + r0.x; g[1] = t0.y + r0.y; g[2] = t0.z + r0.z; g[3] = t0.w + r0.w;
+                    g[4] = t1.x + r1.x; g[5] = t1.y + r1.y; g[6] = t1.z + r1.z; g[7] = t1.w + r1.w;
                 }
+                uint32_t sum = 0;
+                #pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) sum += c[j];
+                uint32_t incl = sum;
+                #pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = shfl_up(incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) warp_sum[warp] = incl;
+                __syncthreads();
+                uint32_t wbase = 0, total = 0;
+                #pragma unroll
+                for (uint32_t w = 0; w < WARPS; ++w) {
+                    if (w == warp) wbase = total;
+                    total += warp_sum[w];
+                }
+                uint32_t run = carry + wbase + incl - sum;
+                carry += total;
+                if (b0 < S) {
+                    uint32_t st[8];
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) { st[j] = run; g[j] -= run; run += c[j]; }
+                    *reinterpret_cast<uint4 *>(cursor + b0) = make_uint4(st[0], st[1], st[2], st[3]);
+                    *reinterpret_cast<uint4 *>(cursor + b0 + 4) = make_uint4(st[4], st[5], st[6], st[7]);
+                    *reinterpret_cast<uint4 *>(delta + b0) = make_uint4(g[0], g[1], g[2], g[3]);
+                    *reinterpret_cast<uint4 *>(delta + b0 + 4) = make_uint4(g[4], g[5], g[6], g[7]);
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
 
-        // re-order by bucket in shared memory
+        // ---- (2) keys: slot from the bucket's cursor, entry stored at the slot ---------------
         #pragma unroll
         for (uint32_t k = 0; k < kTileKeysPerThread; ++k) {
             if (key[k] != 0xffffffffu) {
-                const uint32_t b = key[k] >> 16, rank = key[k] & 0xffffu;
-                const uint32_t local = vec ? ((k / 4) * kTileThreads + tid) * 4 + (k & 3u) : k * kTileThreads + tid;
-                sorted[hist[b] + rank] = (b << 16) | local;
+                const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
+                sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
             }
         }
         __syncthreads();
 
-        // runs of equal buckets are contiguous in `sorted` and in `perm`: coalesced stores
+        // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        for (uint32_t j = tid; j < n_tile; j += kTileThreads) {
+        #pragma unroll 4
+        for (uint32_t j = tid; j < n_tile; j += THREADS) {
             const uint32_t e = sorted[j];
             p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
         }
@@ -554,30 +607,34 @@ static cudaEvent_t mkperm_event() {
     return ev;
 }
 
-/// Developer override for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path
+/// Developer overrides for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path,
+/// DRJIT_B200_MKPERM_TILE_KEYS=16|32 picks the tile size (Ki keys)
 static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_count) {
     static int enabled = -1;
     if (enabled < 0) {
         const char *env = getenv("DRJIT_B200_MKPERM_TILES");
         enabled = env ? atoi(env) != 0 : 1;
     }
-    const uint64_t tiles = ceil_div64(size, kTileKeys);
+    const uint64_t tiles = ceil_div64(size, 512 * kTileKeysPerThread);
     return enabled && n_groups == 1 && bucket_count <= kTileMaxBuckets && size >= (1u << 18) &&
-           tiles * bucket_count * 4 <= ((uint64_t) 2 << 30);
+           tiles * bucket_count * 6 <= ((uint64_t) 2 << 30);
 }
 
+template <uint32_t THREADS>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
                              uint32_t *offsets, uint32_t *hist_out) {
+    constexpr uint32_t TILE = THREADS * kTileKeysPerThread;
     const DeviceProps &dev = device_props();
     MkpermTileParams t{};
     t.values = values; t.perm = perm; t.size = size; t.bucket_count = bucket_count;
+    t.stride = (bucket_count + 7) / 8 * 8;              // rows are read with 128-bit loads
     t.index_base = index_base;
-    t.tiles = (uint32_t) ceil_div64(size, kTileKeys);
+    t.tiles = (uint32_t) ceil_div64(size, TILE);
     t.vec = ((uintptr_t) values % 16) == 0;
 
-    const uint32_t hist_smem = bucket_count * 4,
-                   scatter_smem = bucket_count * 8 + kTileKeys * 4;
+    const uint32_t hist_smem = t.stride * 8,
+                   scatter_smem = t.stride * 8 + TILE * 4;
     uint32_t chunks = std::min(t.tiles, dev.sm_count * 2);
     t.tiles_per_chunk = ceil_div(t.tiles, chunks);
     chunks = ceil_div(t.tiles, t.tiles_per_chunk);
@@ -586,14 +643,17 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     MkpermParams p{};
     p.values = values; p.perm = perm; p.size = size; p.block_size = size;
     p.bucket_count = bucket_count; p.n_groups = 1; p.rows_per_group = chunks;
+    p.row_stride = t.stride;
 
     Scratch scratch(stream);
-    const size_t off_bytes = (size_t) t.tiles * bucket_count * 4,
-                 rows_bytes = (size_t) chunks * bucket_count * 4,
+    const size_t off_bytes = (size_t) t.tiles * t.stride * 4,
+                 cnt_bytes = (size_t) t.tiles * t.stride * 2,
+                 rows_bytes = (size_t) chunks * t.stride * 4,
                  totals_bytes = (size_t) bucket_count * 4;
     auto r256 = [](size_t v) { return (v + 255) & ~(size_t) 255; };
-    scratch.reserve(r256(off_bytes) + r256(rows_bytes) + r256(totals_bytes) + 512);
+    scratch.reserve(r256(off_bytes) + r256(cnt_bytes) + r256(rows_bytes) + r256(totals_bytes) + 512);
     t.tile_off = (uint32_t *) scratch.device(off_bytes);
+    t.tile_cnt = (uint16_t *) scratch.device(cnt_bytes);
     t.rows = p.rows = (uint32_t *) scratch.device(rows_bytes);
     p.totals = (uint32_t *) scratch.device(totals_bytes);
     t.bucket_start = p.totals;
@@ -613,14 +673,14 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
 
     static bool configured = false;
     if (!configured) {
-        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int) (kTileMaxBuckets * 4)));
-        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int) (kTileMaxBuckets * 8 + kTileKeys * 4)));
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int) (kTileMaxBuckets * 8)));
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int) (kTileMaxBuckets * 8 + TILE * 4)));
         configured = true;
     }
 
-    mkperm_tile_hist_kernel<<<chunks, kTileThreads, hist_smem, stream>>>(t);
+    mkperm_tile_hist_kernel<THREADS><<<chunks, THREADS, hist_smem, stream>>>(t);
     DJB_POST_LAUNCH();
     const uint32_t col_tiles = ceil_div(bucket_count, 32);
     mkperm_column_scan_kernel<<<col_tiles, 256, 0, stream>>>(p, col_tiles);
@@ -630,8 +690,12 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     cudaEvent_t ev = want_table ? mkperm_event() : nullptr;
     if (ev)
         DJB_CUDA_CHECK(cudaEventRecord(ev, stream));       // cuda_ts.cpp:953 (before the scatter pass)
-    const uint32_t grid = std::min(t.tiles, dev.sm_count * (scatter_smem <= 100 * 1024 ? 2u : 1u));
-    mkperm_tile_scatter_kernel<<<grid, kTileThreads, scatter_smem, stream>>>(t);
+    mkperm_fold_starts_kernel<<<dim3(ceil_div(bucket_count, 256), std::min(chunks, 32u)), 256, 0, stream>>>(
+        t.rows, t.bucket_start, chunks, bucket_count, t.stride);
+    DJB_POST_LAUNCH();
+    const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
+    const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
+    mkperm_tile_scatter_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t);
     DJB_POST_LAUNCH();
 
     if (!want_table)
@@ -660,8 +724,16 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.bucket_count = bucket_count; p.index_base = index_base;
     p.n_groups = ceil_div(size, block_size);
 
-    if (use_tile_path(p.n_groups, size, bucket_count))
-        return mkperm_tiles(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+    if (use_tile_path(p.n_groups, size, bucket_count)) {
+        static int tile_ki = -1;
+        if (tile_ki < 0) {
+            const char *env = getenv("DRJIT_B200_MKPERM_TILE_KEYS");
+            tile_ki = env ? atoi(env) : 16;
+        }
+        if (tile_ki == 32)
+            return mkperm_tiles<1024>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        return mkperm_tiles<512>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+    }
 
     uint32_t warps = 32;
     const uint32_t smem_budget = dev.smem_optin - 1024;

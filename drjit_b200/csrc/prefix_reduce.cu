@@ -15,11 +15,10 @@
 
 namespace djb {
 
-// Geometry of the 128-bit path, chosen with scripts/sweep_scan.cu (profiles/r1_scan_sweep.md):
+// Geometry of the 128-bit path, chosen with scripts/sweep_scan.cu (profiles/r1b_scan_sweep.md):
 // 32 KiB tiles, 3 TMA stages, 2 CTAs per SM (192 KiB of tiles in flight per SM), aggregates
-// published when a tile lands, look-back by warp 0 of the scan warps.
+// published when a tile lands, windowed carry (scan_kernel.cuh).
 constexpr uint32_t kScanRows = 8, kScanStages = 3, kScanCtas = 2;
-constexpr bool kScanChainWarp = false;
 
 // ---------------------------------------------------------------------------
 //  Host side
@@ -29,9 +28,9 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     using A = acc_t<T>;
     using Geom = ScanGeom<T, VEC, R>;
     const DeviceProps &dev = device_props();
-    auto kernel = prefix_reduce_kernel<T, Op, SEG, VEC, R, STAGES, MIN_CTAS, kScanChainWarp>;
+    auto kernel = prefix_reduce_kernel<T, Op, SEG, VEC, R, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * Geom::TILE_BYTES;
-    constexpr uint32_t threads = ScanRoles<SEG, STAGES, kScanChainWarp>::THREADS;
+    constexpr uint32_t threads = ScanRoles<SEG, STAGES>::THREADS;
 
     static int occupancy = 0; // per instantiation
     if (occupancy == 0) {
@@ -49,7 +48,8 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 
     // Cooperative launch: all CTAs are co-resident, which the static tile schedule relies on
-    const uint32_t grid = std::min(p.tiles, dev.sm_count * (uint32_t) occupancy);
+    // (the windowed carry reads one descriptor per CTA of the grid with <= kScanWindowLoads loads per thread)
+    const uint32_t grid = std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kScanWindowLoads * kScanThreads);
     void *args[] = { (void *) &p };
     DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(threads), args, smem, stream));
     DJB_POST_LAUNCH();

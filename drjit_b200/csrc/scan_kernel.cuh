@@ -3,33 +3,43 @@
  * Host-side dispatch: prefix_reduce.cu; geometry sweep: scripts/sweep_scan.cu.
  *
  * One persistent kernel scans the flat array tile by tile. CTA c processes tiles c, c + G,
- * c + 2G, ... (G = grid size); the grid is launched cooperatively, so all CTAs are co-resident
- * and the look-back always makes progress (the lowest unfinished tile belongs to a running CTA
- * that is working on it). Tiles are chained with a decoupled look-back (Merrill & Garland) in
- * which warp 0 inspects 256 predecessor descriptors per round (8 loads in flight per lane):
- * the sustainable tile rate of a look-back is window / L2 round trip, and a 64-wide window
- * (~60 tiles/us measured) is below what HBM3e delivers (profiles/r1_scan_sweep.md).
+ * c + 2G, ... (G = grid size); the grid is launched cooperatively, so all CTAs are co-resident.
  * Each thread owns ROWS 128-bit units in a warp-striped arrangement, so global stores are
  * coalesced STG.128 without a shared-memory transpose.
  *
  * STAGES > 0: full tiles are fetched by `cp.async.bulk` (TMA, tma.cuh) into a ring of STAGES
  * shared-memory buffers. A stage is refilled as soon as its tile has been moved to registers,
  * i.e. *before* the tile's scan / store phases, so every CTA keeps STAGES tiles in flight no
- * matter which phase it is in. The static schedule is what makes this possible: prefetching
- * does not delay the publication of any tile's aggregate.
- * STAGES >= 2, unsegmented ("CHAIN"): the CTA gets a ninth warp that owns the whole chain
- * protocol. The eight scan warps reduce a tile straight from shared memory as soon as its bulk
- * copy has landed -- STAGES-1 iterations before they scan it -- and hand the eight partials to
- * the chain warp through an mbarrier; the chain warp publishes the aggregate, performs the
- * look-back, publishes the inclusive prefix and leaves the tile's carry in a ring. By the time
- * the scan warps reach the tile its carry has long been computed: neither the L2 round trips of
- * the look-back nor a late bulk copy elsewhere on the chip stall them (profiles/r1_scan_sweep.md).
- * STAGES == 0: direct LDG path (unaligned arrays, element-wise loads when !VEC).
+ * matter which phase it is in.
  *
- * `block_size` only changes where the running value is reset: the scan is segmented with heads
- * at multiples of `block_size`; a tile that contains a head publishes its post-head aggregate
- * as a complete prefix immediately, so short blocks never form a dependency chain. `reverse`
- * mirrors tile and element order; `exclusive` shifts the result by one element at store time.
+ * How a tile learns the reduction of everything before it ("carry"):
+ *
+ * WINDOW (STAGES >= 2, unsegmented; the 128-bit path of every plain prefix reduction). The eight
+ * warps reduce a tile straight from shared memory as soon as its bulk copy has landed -- STAGES-1
+ * iterations before they scan it -- and publish the tile's *aggregate*. Aggregates depend on
+ * nothing but the input, so there is no chain between CTAs at all: CTA c keeps its own running
+ * carry and advances it by the G aggregates of the tiles between its previous tile and the
+ * current one,
+ *        carry(it) = carry(it-1) (+) agg[tile(it-1)] (+) ... (+) agg[tile(it)-1]
+ * (first tile: carry_in (+) agg[0..c)). The G descriptors are loaded by the 256 threads at the top
+ * of the iteration (one or two 8-byte loads per thread, L2 hits) and folded into the block-level
+ * combine that the scan needs anyway, so their latency hides behind the tile's own load/scan
+ * phase and no global round trip is left on the critical path. Every aggregate is read once per
+ * CTA: 8 B x G per 32 KiB tile, ~7 % extra L2 (not DRAM) traffic. Measured against the
+ * decoupled look-back that this replaces (scripts/sweep_scan.cu, profiles/r1b_scan_sweep.md):
+ * the look-back cost 0.85 us per tile that two CTAs per SM could not hide (1.69 ms vs 1.31 ms
+ * with the chain disabled for 2^30 u32); the windowed carry removes it. A side effect: the
+ * association order of a floating-point prefix sum is fixed by (size, grid), so results are
+ * reproducible run to run, which a look-back (whose window depends on timing) cannot offer.
+ *
+ * LOOK-BACK (segmented scans, the element-wise path for unaligned arrays): decoupled look-back
+ * (Merrill & Garland) by warp 0, 320 predecessor descriptors per round with all loads of a round
+ * in flight. `block_size` only changes where the running value is reset: the scan is segmented
+ * with heads at multiples of `block_size`; a tile that contains a head publishes its post-head
+ * aggregate as a complete prefix immediately, so short blocks never form a dependency chain.
+ *
+ * `reverse` mirrors tile and element order; `exclusive` shifts the result by one element at
+ * store time.
  *
  * Reference: resources/block_prefix_reduce.cuh:46-214 (one element per thread, 10-step
  * Hillis-Steele scan with 20 barriers per 1024 elements, every warp spins in the look-back).
@@ -71,27 +81,27 @@ template <typename A> struct TileState<A, 4> {
     }
 };
 
-/// 8-byte accumulators: separate value arrays guarded by a status word (release/acquire)
+/// 8-byte accumulators: {value, status} in one 16-byte word, written and read with a single
+/// 128-bit transaction (STG.E.128.STRONG.GPU / LDG.E.128.STRONG.GPU). A naturally aligned
+/// 16-byte access is performed as one transaction by the memory system -- the same property
+/// CUB's ScanTileState relies on for 8-byte values -- so a reader sees either the old or the
+/// new {value, status} pair, never a mix, and no acquire/release pair (and no second, dependent
+/// load) is needed.
 template <typename A> struct TileState<A, 8> {
-    uint32_t *status_words;
-    uint64_t *aggregates, *prefixes;
-    static size_t bytes(uint32_t tiles) { return ((size_t) tiles * 4 + 255) / 256 * 256 + (size_t) tiles * 16; }
-    __host__ __device__ void bind(void *base, uint32_t tiles) {
-        status_words = (uint32_t *) base;
-        aggregates = (uint64_t *) ((uint8_t *) base + ((size_t) tiles * 4 + 255) / 256 * 256);
-        prefixes = aggregates + tiles;
-    }
+    ulonglong2 *words;
+    static size_t bytes(uint32_t tiles) { return (size_t) tiles * 16; }
+    __host__ __device__ void bind(void *base, uint32_t) { words = (ulonglong2 *) base; }
     __device__ __forceinline__ void publish(uint32_t tile, uint32_t status, A value) {
         uint64_t bits;
         memcpy(&bits, &value, 8);
-        st_relaxed_u64((status == kPrefix ? prefixes : aggregates) + tile, bits);
-        st_release_u32(status_words + tile, status);
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};"
+                     :: "l"(words + tile), "l"(bits), "l"((uint64_t) status) : "memory");
     }
     __device__ __forceinline__ void load(uint32_t tile, uint32_t &status, A &value) {
-        status = ld_acquire_u32(status_words + tile);
-        uint64_t bits = 0;
-        if (status != kInvalid)
-            bits = ld_relaxed_u64((status == kPrefix ? prefixes : aggregates) + tile);
+        uint64_t bits, st;
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];"
+                     : "=l"(bits), "=l"(st) : "l"(words + tile) : "memory");
+        status = (uint32_t) st;
         memcpy(&value, &bits, 8);
     }
 };
@@ -120,14 +130,14 @@ template <typename T, bool VEC, uint32_t R> struct ScanGeom {
     static constexpr uint32_t TILE_BYTES = TILE * sizeof(T);
 };
 
-/// The chain warp exists for unsegmented scans with at least two TMA stages
-template <bool SEG, uint32_t STAGES, bool CHAINW> struct ScanRoles {
-    static constexpr bool EARLY = STAGES >= 2 && !SEG;      // aggregates published when the copy lands
-    static constexpr bool CHAIN = EARLY && CHAINW;          // ... and a dedicated chain warp
-    static constexpr uint32_t THREADS = kScanThreads + (CHAIN ? 32 : 0);
+/// Unsegmented scans with at least two TMA stages publish aggregates early and use the windowed carry
+template <bool SEG, uint32_t STAGES> struct ScanRoles {
+    static constexpr bool WINDOW = STAGES >= 2 && !SEG;
+    static constexpr uint32_t THREADS = kScanThreads;
 };
+constexpr uint32_t kScanWindowLoads = 3;    // descriptors per thread: grids of up to 768 CTAs
 
-/// Barrier among the eight scan warps only (the chain warp never takes part)
+/// Barrier among the eight scan warps
 __device__ __forceinline__ void scan_warps_sync() {
     asm volatile("bar.sync 1, %0;" :: "n"(kScanThreads) : "memory");
 }
@@ -178,8 +188,8 @@ __device__ __forceinline__ A scan_lookback(TileState<A> &state, uint32_t tile, u
     return excl;
 }
 
-template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS, bool CHAINW = true>
-__global__ void __launch_bounds__((ScanRoles<SEG, STAGES, CHAINW>::THREADS), MIN_CTAS)
+template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS>
+__global__ void __launch_bounds__(kScanThreads, MIN_CTAS)
 prefix_reduce_kernel(const PrefixParams p) {
     using A = acc_t<T>;
     using Geom = ScanGeom<T, VEC, R>;
@@ -187,20 +197,16 @@ prefix_reduce_kernel(const PrefixParams p) {
     constexpr uint32_t ROWS = Geom::ROWS;   // units per thread
     constexpr uint32_t TILE = Geom::TILE;
     constexpr bool STAGED = STAGES > 0;
-    constexpr bool EARLY = ScanRoles<SEG, STAGES, CHAINW>::EARLY;
-    constexpr bool CHAIN = ScanRoles<SEG, STAGES, CHAINW>::CHAIN;
+    constexpr bool WINDOW = ScanRoles<SEG, STAGES>::WINDOW;
     constexpr uint32_t NS = STAGED ? STAGES : 1;
     static_assert(!STAGED || VEC, "staged tiles need the 128-bit path");
     const A ident = Op::template identity<A>();
 
     extern __shared__ __align__(128) uint8_t stage_mem[];   // STAGES x TILE_BYTES
     __shared__ uint64_t full_bar[NS];       // TMA: tile has landed in its stage
-    __shared__ uint64_t early_bar[NS];      // CHAIN: the 8 partial aggregates of a tile are in early_val
-    __shared__ uint64_t carry_bar[NS];      // CHAIN: the tile's carry is in carry_ring
-    __shared__ A early_val[NS][kScanWarps];
-    __shared__ A carry_ring[NS];
-    __shared__ A agg_ring[NS];              // chain warp private
+    __shared__ A early_val[NS][kScanWarps]; // WINDOW: per-warp partial aggregates of a landed tile
     __shared__ A warp_val[kScanWarps];
+    __shared__ A win_val[kScanWarps];       // WINDOW: per-warp partial sums of the carry window
     __shared__ uint32_t warp_flag[kScanWarps];
     __shared__ A carry_smem;
 
@@ -236,11 +242,8 @@ prefix_reduce_kernel(const PrefixParams p) {
     if constexpr (STAGED) {
         if (tid == kScanFetchTid) {
             #pragma unroll
-            for (uint32_t s = 0; s < STAGES; ++s) {
+            for (uint32_t s = 0; s < STAGES; ++s)
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&early_bar[s], kScanWarps);
-                mbar_init(&carry_bar[s], 1);
-            }
             fence_proxy_async();
             policy = policy_evict_first();
             #pragma unroll
@@ -249,58 +252,8 @@ prefix_reduce_kernel(const PrefixParams p) {
         __syncthreads();
     }
 
-    // ===================================================================================
-    //  Chain warp: aggregate -> look-back -> inclusive prefix -> carry, one tile after another
-    // ===================================================================================
-    if constexpr (CHAIN) {
-        if (warp == kScanWarps) {
-            // Step i publishes the aggregate of the CTA's i-th tile (its partials arrive when the
-            // scan warps *start* iteration i-(STAGES-1)) and then resolves the carry of tile
-            // i-(STAGES-1), which the scan warps need at the *end* of that iteration. Aggregates
-            // are therefore STAGES-1 iterations old when a look-back reads them, and the
-            // look-back's L2 round trips overlap the scan warps' own work on the tile.
-            // With three or more stages the carry is resolved one iteration earlier still (LAG =
-            // STAGES-2), which takes the look-back off the scan warps' critical path entirely.
-            constexpr uint32_t LAG = STAGES >= 3 ? STAGES - 2 : STAGES - 1;
-            const uint64_t last = p.tiles - 1;
-            const uint32_t n_cta = blockIdx.x > last ? 0u : (uint32_t) ((last - blockIdx.x) / gridDim.x) + 1u;
-            for (uint32_t step = 0; step < n_cta + LAG; ++step) {
-                if (step < n_cta && tile_is_staged(tile_of(step))) {
-                    const uint32_t s = step % NS;
-                    mbar_wait(&early_bar[s], (step / NS) & 1u);
-                    A agg = lane < kScanWarps ? early_val[s][lane] : ident;
-                    agg = WarpReduce<Op, A>::template run<32>(agg);
-                    if (lane == 0) {
-                        agg_ring[s] = agg;
-                        if (tile_of(step) != 0)
-                            state.publish((uint32_t) tile_of(step), kAggregate, agg);
-                    }
-                }
-                if (step >= LAG) {
-                    const uint32_t k = step - LAG, s = k % NS;
-                    const uint64_t t64 = tile_of(k);
-                    const uint32_t tile = (uint32_t) t64;
-                    A excl = ident;
-                    if (tile == 0) {
-                        if (p.carry_in) excl = to_acc<A>(*(const T *) p.carry_in);
-                    } else if (!(p.debug & 1)) {
-                        excl = scan_lookback<Op, A>(state, tile, lane);
-                    }
-                    if (lane == 0) {
-                        if (tile_is_staged(t64))       // (only a ragged last tile is not staged)
-                            state.publish(tile, kPrefix, Op::template apply<A>(excl, agg_ring[s]));
-                        carry_ring[s] = excl;
-                        mbar_arrive(&carry_bar[s]);
-                    }
-                }
-                __syncwarp();
-            }
-            return;
-        }
-    }
-
-    // CHAIN, scan warps: per-warp partial aggregate of this CTA's k-th tile, read from its stage
-    // as soon as it has landed and handed to the chain warp
+    // WINDOW: per-warp partial aggregate of this CTA's k-th tile, read from its stage as soon as
+    // it has landed; after the next barrier warp 0 folds the partials and publishes the aggregate
     auto early_reduce = [&](uint32_t k) {
         const uint64_t t64 = tile_of(k);
         if (!tile_is_staged(t64))
@@ -318,34 +271,31 @@ prefix_reduce_kernel(const PrefixParams p) {
                 acc = Op::template apply<A>(acc, to_acc<A>(v.v[e]));
         }
         acc = WarpReduce<Op, A>::template run<32>(acc);
-        if (lane == 0) {
+        if (lane == 0)
             early_val[s][warp] = acc;
-            if constexpr (CHAIN) mbar_arrive(&early_bar[s]);
-        }
     };
-    // EARLY without a chain warp: warp 0 folds the partials after a barrier and publishes
     auto early_publish = [&](uint32_t k) {
         const uint64_t t64 = tile_of(k);
-        if (!tile_is_staged(t64) || t64 == 0)
+        if (!tile_is_staged(t64))
             return;
         A v = lane < kScanWarps ? early_val[k % NS][lane] : ident;
         v = WarpReduce<Op, A>::template run<32>(v);
         if (lane == 0)
             state.publish((uint32_t) t64, kAggregate, v);
     };
-    if constexpr (EARLY) {
+    if constexpr (WINDOW) {
         for (uint32_t k = 0; k + 1 < STAGES; ++k) {
             early_reduce(k);
-            if constexpr (!CHAIN) {
-                scan_warps_sync();
-                if (warp == 0) early_publish(k);
-            }
+            scan_warps_sync();
+            if (warp == 0) early_publish(k);
         }
     }
 
-    // ===================================================================================
-    //  Scan warps
-    // ===================================================================================
+    A carry = ident;            // WINDOW: reduction of everything before the current tile
+    if constexpr (WINDOW) {
+        if (p.carry_in) carry = to_acc<A>(*(const T *) p.carry_in);
+    }
+
     for (uint32_t it = 0;; ++it) {
         const uint64_t tile64 = tile_of(it);
         if (tile64 >= p.tiles)
@@ -355,13 +305,28 @@ prefix_reduce_kernel(const PrefixParams p) {
         const uint64_t tile_base = tile64 * TILE;   // scan-order position
         const bool staged = tile_is_staged(tile64);
 
+        // ---- WINDOW: start loading the aggregates between the previous tile and this one ----
+        // (published at least STAGES-1 iterations ago; consumed before the combine barrier)
+        uint32_t win_status[kScanWindowLoads];
+        A win_value[kScanWindowLoads];
+        const uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x,
+                       win_n = (p.debug & 1) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
+        if constexpr (WINDOW) {
+            #pragma unroll
+            for (uint32_t j = 0; j < kScanWindowLoads; ++j) {
+                win_status[j] = kAggregate; win_value[j] = ident;
+                const uint32_t o = j * kScanThreads + tid;
+                if (o < win_n) state.load(win_lo + o, win_status[j], win_value[j]);
+            }
+        }
+
         // ---- load + thread-local segmented scan ----------------------------------
         A incl[ROWS][V];
         uint32_t head_mask[ROWS];   // bit e: element e of the unit starts a segment
         A unit_val[ROWS];           // aggregate after the last head of the unit
 
         Vec16<T> raw[ROWS];
-        if constexpr (EARLY)
+        if constexpr (WINDOW)
             early_reduce(it + STAGES - 1);
         if constexpr (STAGED) {
             if (staged) {
@@ -377,7 +342,7 @@ prefix_reduce_kernel(const PrefixParams p) {
             scan_warps_sync();                       // stage is free again
             if (tid == kScanFetchTid)                // refill before the phases below
                 issue(stage, tile64 + (uint64_t) STAGES * gridDim.x);
-            if constexpr (EARLY && !CHAIN) {
+            if constexpr (WINDOW) {
                 if (warp == 0) early_publish(it + STAGES - 1);
             }
         }
@@ -467,6 +432,22 @@ prefix_reduce_kernel(const PrefixParams p) {
             warp_val[warp] = wcarry;
             warp_flag[warp] = wflag;
         }
+        if constexpr (WINDOW) {
+            // fold this thread's share of the carry window (an aggregate that is not there yet
+            // belongs to a CTA that runs behind: poll)
+            A w = ident;
+            #pragma unroll
+            for (uint32_t j = 0; j < kScanWindowLoads; ++j) {
+                const uint32_t o = j * kScanThreads + tid;
+                while (win_status[j] == kInvalid) {
+                    __nanosleep(20);
+                    state.load(win_lo + o, win_status[j], win_value[j]);
+                }
+                w = Op::template apply<A>(w, win_value[j]);
+            }
+            w = WarpReduce<Op, A>::template run<32>(w);
+            if (lane == 0) win_val[warp] = w;
+        }
         scan_warps_sync();
 
         // ---- CTA-level: prefix over the preceding warps, tile aggregate -----------
@@ -483,9 +464,13 @@ prefix_reduce_kernel(const PrefixParams p) {
 
         // ---- the tile's carry ----------------------------------------------------------
         A tile_carry;
-        if constexpr (CHAIN) {
-            mbar_wait(&carry_bar[stage], (it / NS) & 1u);     // computed by the chain warp long ago
-            tile_carry = carry_ring[stage];
+        if constexpr (WINDOW) {
+            #pragma unroll
+            for (uint32_t w = 0; w < kScanWarps; ++w)
+                carry = Op::template apply<A>(carry, win_val[w]);
+            tile_carry = carry;
+            if (!staged && tid == 0)     // (a ragged last tile was not published early; keeps the
+                state.publish(tile, kAggregate, tv);  //  descriptor array fully defined)
         } else {
             // decoupled look-back by warp 0 while the other warps wait
             if (warp == 0) {
@@ -499,7 +484,7 @@ prefix_reduce_kernel(const PrefixParams p) {
                 } else {
                     if (lane == 0 && tf)
                         state.publish(tile, kPrefix, tv);      // complete: the segment starts inside
-                    else if (lane == 0 && !(EARLY && staged))      // (EARLY: published when the copy landed)
+                    else if (lane == 0)
                         state.publish(tile, kAggregate, tv);
                     excl = scan_lookback<Op, A>(state, tile, lane);
                     if (lane == 0 && !tf)

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <vector>
 
@@ -39,9 +40,12 @@ static uint32_t *g_out, *g_count;
 static unsigned long long *g_err;
 static double g_density;
 
+static const char *g_filter = nullptr;
+
 template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t CTAS_PER_SM = 0>
 void run(uint64_t n, const char *label) {
     constexpr uint32_t TILE = kCompThreads * ROWS * kCompUnit;
+    if (g_filter && !strstr(label, g_filter)) return;
     auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * TILE;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -89,6 +93,7 @@ int main(int argc, char **argv) {
     const uint32_t thr = argc > 2 ? atoi(argv[2]) : 128;
     const uint64_t n = 1ull << lg;
     g_density = thr / 256.0;
+    if (argc > 3 && argv[3][0]) g_filter = argv[3];
     CK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, 0));
     CK(cudaMalloc(&g_in, n)); CK(cudaMalloc(&g_out, n * 4));
     CK(cudaMalloc(&g_scratch, 64 << 20)); CK(cudaMalloc(&g_err, 16)); CK(cudaMalloc(&g_count, 4));
@@ -97,17 +102,15 @@ int main(int argc, char **argv) {
     CK(cudaDeviceSynchronize());
     printf("compress, n = 2^%d, density %.3f, %d SMs\n", lg, g_density, g_sms);
 
-    run<8, 0, 3>(n, "direct ROWS=8");
-    run<8, 1, 3>(n, "staged ROWS=8 S=1 min3");
-    run<16, 1, 3>(n, "staged ROWS=16 S=1 min3");
-    run<4, 2, 4>(n, "early ROWS=4 S=2 min4");
-    run<4, 4, 3>(n, "early ROWS=4 S=4 min3");
-    run<4, 6, 2>(n, "early ROWS=4 S=6 min2");
-    run<8, 2, 3>(n, "early ROWS=8 S=2 min3");
-    run<8, 2, 2>(n, "early ROWS=8 S=2 min2");
-    run<8, 3, 2>(n, "early ROWS=8 S=3 min2");
-    run<8, 3, 1, 1>(n, "early ROWS=8 S=3 occ1");
-    run<16, 2, 1>(n, "early ROWS=16 S=2 min1");
-    run<16, 3, 1>(n, "early ROWS=16 S=3 min1");
+    run<8, 0, 3>(n, "direct ROWS=8 min3");
+    run<4, 2, 4>(n, "ROWS=4 S=2 min4");
+    run<4, 4, 3>(n, "ROWS=4 S=4 min3");
+    run<8, 1, 3>(n, "ROWS=8 S=1 min3");
+    run<8, 1, 4>(n, "ROWS=8 S=1 min4");
+    run<8, 2, 3>(n, "ROWS=8 S=2 min3");
+    run<8, 2, 2>(n, "ROWS=8 S=2 min2");
+    run<8, 3, 2>(n, "ROWS=8 S=3 min2");
+    run<16, 1, 2>(n, "ROWS=16 S=1 min2");
+    run<16, 2, 1>(n, "ROWS=16 S=2 min1");
     return 0;
 }

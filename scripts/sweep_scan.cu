@@ -36,14 +36,14 @@ static unsigned long long *g_err;
 static const char *g_filter = nullptr;
 static int g_debug = 0;
 
-template <uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS, bool CHAINW = true>
+template <uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS>
 void run(uint64_t n, const char *label) {
     constexpr uint32_t CTAS_PER_SM = 0;
     using Geom = ScanGeom<uint32_t, true, R>;
     if (g_filter && !strstr(label, g_filter)) return;
-    auto kernel = prefix_reduce_kernel<uint32_t, OpAdd, false, true, R, STAGES, MIN_CTAS, CHAINW>;
+    auto kernel = prefix_reduce_kernel<uint32_t, OpAdd, false, true, R, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * Geom::TILE_BYTES;
-    constexpr uint32_t threads = ScanRoles<false, STAGES, CHAINW>::THREADS;
+    constexpr uint32_t threads = ScanRoles<false, STAGES>::THREADS;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
@@ -94,22 +94,16 @@ int main(int argc, char **argv) {
     CK(cudaDeviceSynchronize());
     printf("exclusive u32 prefix sum, n = 2^%d, %d SMs, debug=%d\n", lg, g_sms, g_debug);
 
-    run<8, 0, 3>(n, "direct R=8 min3");
-    run<8, 1, 3>(n, "staged R=8 S=1 min3");
-    // early aggregates, look-back inline by warp 0
-    run<4, 4, 3, false>(n, "inline R=4 S=4 min3");
-    run<8, 2, 3, false>(n, "inline R=8 S=2 min3");
-    run<8, 2, 2, false>(n, "inline R=8 S=2 min2");
-    run<8, 3, 2, false>(n, "inline R=8 S=3 min2");
-    run<16, 2, 1, false>(n, "inline R=16 S=2 min1");
-    // early aggregates + dedicated chain warp
-    run<4, 4, 3, true>(n, "chain R=4 S=4 min3");
-    run<4, 6, 2, true>(n, "chain R=4 S=6 min2");
-    run<8, 2, 3, true>(n, "chain R=8 S=2 min3");
-    run<8, 2, 2, true>(n, "chain R=8 S=2 min2");
-    run<8, 3, 2, true>(n, "chain R=8 S=3 min2");
-    run<8, 6, 1, true>(n, "chain R=8 S=6 min1");
-    run<16, 2, 1, true>(n, "chain R=16 S=2 min1");
-    run<16, 3, 1, true>(n, "chain R=16 S=3 min1");
+    // STAGES < 2: decoupled look-back; STAGES >= 2: early aggregates + windowed carry
+    run<8, 0, 3>(n, "lookback direct R=8 min3");
+    run<8, 1, 3>(n, "lookback staged R=8 S=1 min3");
+    run<4, 2, 4>(n, "window R=4 S=2 min4");
+    run<4, 3, 4>(n, "window R=4 S=3 min4");
+    run<4, 4, 3>(n, "window R=4 S=4 min3");
+    run<8, 2, 3>(n, "window R=8 S=2 min3");
+    run<8, 2, 2>(n, "window R=8 S=2 min2");
+    run<8, 3, 2>(n, "window R=8 S=3 min2");
+    run<16, 2, 1>(n, "window R=16 S=2 min1");
+    run<16, 3, 1>(n, "window R=16 S=3 min1");
     return 0;
 }

@@ -14,7 +14,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import drjit_b200 as dr  # noqa: E402
 from drjit_b200 import ReduceOp, VarType, ops  # noqa: E402
 
-PEAK = 6451.8
+def _peak():
+    import json
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+PEAK = _peak()
 
 
 WARM = 3
