@@ -68,7 +68,7 @@ uint32_t compress(cudaStream_t stream, const uint8_t *in, uint32_t size, uint32_
     // small tiles keep all SMs busy on small masks (cuda_ts.cpp:693 draws its line at 4096)
     const DeviceProps &dev = device_props();
     const bool big = (uint64_t) size >= (uint64_t) kCompThreads * kCompRowsBig * kCompUnit * dev.sm_count * 4;
-    if (big && aligned)  launch_compress<kCompRowsBig, 2, 3>(stream, p, scratch);
+    if (big && aligned)  launch_compress<kCompRowsBig, 1, 3>(stream, p, scratch);
     else if (big)        launch_compress<kCompRowsBig, 0, 3>(stream, p, scratch);
     else if (aligned)    launch_compress<kCompRowsSmall, 2, 4>(stream, p, scratch);
     else                 launch_compress<kCompRowsSmall, 0, 4>(stream, p, scratch);

@@ -25,6 +25,7 @@
  *   GLOBAL : global-memory atomics for bucket counts beyond shared memory ("large").
  */
 #include "common.cuh"
+#include "tma.cuh"
 #include "runtime.h"
 
 #include <cstdlib>
@@ -429,6 +430,8 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
         const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
         uint32_t key[kTileKeysPerThread];
         tile_load_keys<THREADS>(p, tile_base, n_tile, key);      // loads in flight across the barrier
+        if (tid == 0 && p.vec && tile + 1 < end && (uint64_t) (tile + 2) * TILE <= p.size)
+            bulk_prefetch_l2(p.values + (uint64_t) (tile + 1) * TILE, TILE * 4);
         __syncthreads();                                    // previous tile's atomics are done
         snapshot(tile);
         __syncthreads();
@@ -473,6 +476,17 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         uint32_t key[kTileKeysPerThread];
         tile_load_keys<THREADS>(p, tile_base, n_tile, key);     // in flight during the bin phase
+        // Ask L2 for everything the next tile of this CTA will read, so that its loads see an L2
+        // round trip instead of DRAM latency (the kernel was latency-bound: profiles/r1d)
+        if (tid == 0) {
+            const uint64_t next = (uint64_t) tile + gridDim.x;
+            if (next < p.tiles) {
+                if (p.vec && (next + 1) * TILE <= p.size)
+                    bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
+                bulk_prefetch_l2(p.tile_off + next * S, S * 4);
+                bulk_prefetch_l2(p.tile_cnt + next * S, S * 2);
+            }
+        }
 
         // ---- (1) bins: thread t owns 8 consecutive buckets per round ----------------------
         {
@@ -725,12 +739,16 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.n_groups = ceil_div(size, block_size);
 
     if (use_tile_path(p.n_groups, size, bucket_count)) {
+        // 32 Ki-key tiles (1 CTA/SM) double the length of the runs written per bucket and win when
+        // there are many buckets; 16 Ki-key tiles (2 CTAs/SM) overlap better and win for few
+        // (measured at 2^26 keys: 4096 buckets 0.352 vs 0.520 ms, 256 buckets 0.243 vs 0.227 ms)
         static int tile_ki = -1;
         if (tile_ki < 0) {
             const char *env = getenv("DRJIT_B200_MKPERM_TILE_KEYS");
-            tile_ki = env ? atoi(env) : 16;
+            tile_ki = env ? atoi(env) : 0;
         }
-        if (tile_ki == 32)
+        const bool big = tile_ki ? tile_ki == 32 : bucket_count >= 1024;
+        if (big)
             return mkperm_tiles<1024>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         return mkperm_tiles<512>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
     }

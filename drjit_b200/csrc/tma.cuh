@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
                  : "memory");
 }
 
+/// Asks L2 to fetch `bytes` (multiple of 16) starting at the 16-byte aligned address `gmem`:
+/// one instruction, no destination, no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gmem), "r"(bytes) : "memory");
+}
+
 /// 128-bit shared-memory load
 __device__ __forceinline__ uint4 lds128(const void *p) {
     uint4 r;

@@ -41,6 +41,7 @@ static unsigned long long *g_err;
 static double g_density;
 
 static const char *g_filter = nullptr;
+static int g_debug = 0;
 
 template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t CTAS_PER_SM = 0>
 void run(uint64_t n, const char *label) {
@@ -56,7 +57,7 @@ void run(uint64_t n, const char *label) {
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kernel));
 
     CompressParams p{};
-    p.in = g_in; p.out = g_out; p.size = (uint32_t) n; p.index_base = 0;
+    p.in = g_in; p.out = g_out; p.size = (uint32_t) n; p.index_base = 0; p.debug = (uint32_t) g_debug;
     p.tiles = (uint32_t) ((n + TILE - 1) / TILE);
     p.state = (uint64_t *) g_scratch; p.count_out = g_count;
     const size_t state_bytes = (size_t) p.tiles * 8;
@@ -77,7 +78,7 @@ void run(uint64_t n, const char *label) {
     }
     std::sort(ts.begin(), ts.end());
     CK(cudaMemset(g_err, 0, 16));
-    check<<<g_sms * 8, 256>>>(g_in, g_out, n, g_count, g_err, g_err + 1);
+    if (!g_debug) check<<<g_sms * 8, 256>>>(g_in, g_out, n, g_count, g_err, g_err + 1);
     unsigned long long res[2]; CK(cudaMemcpy(res, g_err, 16, cudaMemcpyDeviceToHost));
     uint32_t cnt; CK(cudaMemcpy(&cnt, g_count, 4, cudaMemcpyDeviceToHost));
     const bool ok = res[0] == 0 && res[1] == cnt;
@@ -94,6 +95,7 @@ int main(int argc, char **argv) {
     const uint64_t n = 1ull << lg;
     g_density = thr / 256.0;
     if (argc > 3 && argv[3][0]) g_filter = argv[3];
+    if (argc > 4) g_debug = atoi(argv[4]);
     CK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, 0));
     CK(cudaMalloc(&g_in, n)); CK(cudaMalloc(&g_out, n * 4));
     CK(cudaMalloc(&g_scratch, 64 << 20)); CK(cudaMalloc(&g_err, 16)); CK(cudaMalloc(&g_count, 4));
