@@ -288,7 +288,8 @@ compress_kernel(const CompressParams p) {
                             sts_u16(wa + 2 * j, and_or((uint32_t) qq, 15u, lane16));
                 }
                 __syncwarp();
-                // coalesced copy-out, 128 slots per round
+                // coalesced copy-out, 128 slots per round (a two-slots-per-lane LDS.32/STG.64
+                // variant was 18 % slower: profiles/r1f_sweep_compress_paired_copyout.txt)
                 const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
                 for (uint32_t s0 = 0; s0 < n; s0 += 128) {
                     #pragma unroll

@@ -130,9 +130,9 @@ template <typename T, bool VEC, uint32_t R> struct ScanGeom {
     static constexpr uint32_t TILE_BYTES = TILE * sizeof(T);
 };
 
-/// Unsegmented scans with at least two TMA stages publish aggregates early and use the windowed carry
+/// Scans with at least two TMA stages publish aggregates early and use the windowed carry
 template <bool SEG, uint32_t STAGES> struct ScanRoles {
-    static constexpr bool WINDOW = STAGES >= 2 && !SEG;
+    static constexpr bool WINDOW = STAGES >= 2;
     static constexpr uint32_t THREADS = kScanThreads;
 };
 constexpr uint32_t kScanWindowLoads = 3;    // descriptors per thread: grids of up to 768 CTAs
@@ -225,6 +225,14 @@ prefix_reduce_kernel(const PrefixParams p) {
         return (uint32_t) (x - q * bs);
     };
 
+    // SEG: largest head position (scan order) <= x, or -1 if there is none. Forward scans have
+    // heads at multiples of block_size; mirrored scans where (size - position) is one.
+    auto last_head_le = [&](uint64_t x) -> int64_t {
+        const uint32_t d = rev ? mod_bs((uint64_t) size - x) : mod_bs(x);
+        const uint32_t k = rev ? (d == 0 ? 0u : bs - d) : d;
+        return (int64_t) x - (int64_t) k;
+    };
+
     // ---- tile acquisition (static round-robin schedule) ---------------------------------
     uint64_t policy = 0;
     auto tile_of = [&](uint32_t k) -> uint64_t { return (uint64_t) blockIdx.x + (uint64_t) k * gridDim.x; };
@@ -261,14 +269,24 @@ prefix_reduce_kernel(const PrefixParams p) {
         const uint32_t s = k % NS;
         mbar_wait(&full_bar[s], (k / NS) & 1u);
         const uint8_t *src = stage_mem + (size_t) s * Geom::TILE_BYTES;
+        // SEG: the aggregate only covers what follows the tile's last head (tile-local position)
+        uint32_t first = 0;
+        if constexpr (SEG) {
+            const int64_t h = last_head_le((t64 + 1) * TILE - 1);
+            if (h > (int64_t) (t64 * TILE)) first = (uint32_t) (h - (int64_t) (t64 * TILE));
+        }
         A acc = ident;
         #pragma unroll
         for (uint32_t r = 0; r < ROWS; ++r) {
+            const uint32_t u = (warp * ROWS + r) * 32 + lane;       // unit in scan order
             Vec16<T> v;
-            *reinterpret_cast<uint4 *>(&v) = lds128(src + ((warp * ROWS + r) * 32 + lane) * 16);
+            *reinterpret_cast<uint4 *>(&v) = lds128(src + (SEG && rev ? Geom::TILE_BYTES - (u + 1) * 16 : u * 16));
             #pragma unroll
-            for (uint32_t e = 0; e < V; ++e)
-                acc = Op::template apply<A>(acc, to_acc<A>(v.v[e]));
+            for (uint32_t e = 0; e < V; ++e) {
+                const A x = to_acc<A>(SEG && rev ? v.v[V - 1 - e] : v.v[e]);
+                if (!SEG || u * V + e >= first)
+                    acc = Op::template apply<A>(acc, x);
+            }
         }
         acc = WarpReduce<Op, A>::template run<32>(acc);
         if (lane == 0)
@@ -309,8 +327,18 @@ prefix_reduce_kernel(const PrefixParams p) {
         // (published at least STAGES-1 iterations ago; consumed before the combine barrier)
         uint32_t win_status[kScanWindowLoads];
         A win_value[kScanWindowLoads];
-        const uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x,
-                       win_n = (p.debug & 1) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
+        uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x;
+        bool win_reset = false;     // SEG: a head lies inside the window, the running carry restarts there
+        if constexpr (SEG && WINDOW) {
+            if (tile != 0) {
+                const int64_t h = last_head_le(tile_base - 1);
+                if (h >= 0 && (uint32_t) ((uint64_t) h / TILE) >= win_lo) {
+                    win_lo = (uint32_t) ((uint64_t) h / TILE);
+                    win_reset = true;
+                }
+            }
+        }
+        const uint32_t win_n = (p.debug & 1) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
         if constexpr (WINDOW) {
             #pragma unroll
             for (uint32_t j = 0; j < kScanWindowLoads; ++j) {
@@ -465,6 +493,7 @@ prefix_reduce_kernel(const PrefixParams p) {
         // ---- the tile's carry ----------------------------------------------------------
         A tile_carry;
         if constexpr (WINDOW) {
+            if (SEG && win_reset) carry = ident;
             #pragma unroll
             for (uint32_t w = 0; w < kScanWarps; ++w)
                 carry = Op::template apply<A>(carry, win_val[w]);

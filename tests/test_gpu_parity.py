@@ -287,6 +287,36 @@ def test_prefix_sum_2_30_properties():
     assert np.array_equal(to_np(out, "u32"), exp)
 
 
+@pytest.mark.parametrize("vt", ["u8", "u32", "u64", "i32", "i64"])
+def test_prefix_windowed_carry_many_tiles(vt):
+    """Unsegmented scans on the TMA path with more tiles than CTAs (every CTA advances its carry
+    by a full window of 296 aggregates several times), all four variants, ragged last tile; exact."""
+    n = (1 << 23) + 12345 if vt != "u8" else (1 << 24) + 77
+    x = make_input(vt, n); xd = to_dev(x, vt)
+    for op in ("add", "max"):
+        for ex, rev in ((1, 0), (0, 0), (1, 1)):
+            if rev and n % (16 // x.itemsize):
+                continue        # (mirrored vectors need the array end on a vector boundary: slow path, tested elsewhere)
+            got = to_np(dr.block_prefix_reduce(OPS[op], xd, n, ex, rev, vt=VT[vt]), vt)
+            assert np.array_equal(got, capi.block_prefix_reduce(vt, op, x, n, ex, rev)), (vt, op, ex, rev)
+    n2 = n - n % 16
+    got = to_np(dr.block_prefix_reduce(OPS["add"], xd[:n2], n2, 1, 1, vt=VT[vt]), vt)
+    assert np.array_equal(got, capi.block_prefix_reduce(vt, "add", x[:n2], n2, 1, 1))
+
+
+@pytest.mark.parametrize("vt", ["f32", "f64"])
+def test_prefix_sum_float_large_and_reproducible(vt):
+    """f32: relative 1e-6*log2(N) against an f64 oracle (north_star); the windowed carry fixes
+    the association order, so two runs must agree bit for bit."""
+    n = (1 << 24) + 3
+    x = make_input(vt, n); xd = to_dev(x, vt)
+    a = dr.block_prefix_reduce(ReduceOp.Add, xd, n, False, False, vt=VT[vt])
+    b = dr.block_prefix_reduce(ReduceOp.Add, xd, n, False, False, vt=VT[vt])
+    assert torch.equal(a, b)
+    exp = np.cumsum(x.astype(np.float64))
+    assert_close(to_np(a, vt), exp, vt, n, f"{vt} inclusive prefix sum of {n}")
+
+
 # --------------------------------------------------------------------------- compress
 def test_compress_reference_grid():
     """reductions.cpp:269-313: sizes 23 i^3 + 1, n_ones 23 j^3 + 1 random ones, exact list + count"""
@@ -314,6 +344,20 @@ def test_compress_large(size, density):
     assert np.array_equal(to_np(dr.compress(buf[5:]), "u32"), exp)
     # the mask must not be modified (the reference zero-pads it, we do not)
     assert torch.equal(buf[5:], m)
+
+
+@pytest.mark.parametrize("density", [0.003, 0.3, 0.97])
+def test_compress_many_tiles_ragged_unaligned(density):
+    """More tiles than CTAs (windowed carry over full windows), ragged tail, TMA and direct
+    (unaligned mask) paths, sparse- and dense-row expansion; exact."""
+    n = (1 << 25) + 4321
+    rng = np.random.default_rng(7)
+    m = (rng.random(n + 3) < density).astype(np.uint8)
+    m[::977] *= 7                    # any non-zero byte counts (cuda_ts.cpp:683-763 treats the mask as bool)
+    md = torch.from_numpy(m).cuda()
+    for off in (0, 3):
+        got = to_np(dr.compress(md[off:off + n]), "u32")
+        assert np.array_equal(got, np.flatnonzero(m[off:off + n]).astype(np.uint32)), (density, off)
 
 
 def test_compress_literals_and_golden():
