@@ -273,7 +273,8 @@ compress_kernel(const CompressParams p) {
                 // 64-bit nibble stream: positions of the set bits of m, ascending
                 const uint32_t lo = lut[m & 0xffu], hi = lut[m >> 8] + 0x88888888u;
                 const uint64_t q = (uint64_t) lo | ((uint64_t) hi << (4 * __popc(m & 0xffu)));
-                const uint32_t wa = stg_addr + 2 * r;
+                uint32_t wa = stg_addr + 2 * r;
+                asm volatile("" : "+r"(wa));      // (keeps ptxas from re-deriving the address per store)
                 if (n > 64) {
                     #pragma unroll
                     for (uint32_t j = 0; j < kCompUnit; ++j)
@@ -291,13 +292,20 @@ compress_kernel(const CompressParams p) {
                 // coalesced copy-out, 128 slots per round (a two-slots-per-lane LDS.32/STG.64
                 // variant was 18 % slower: profiles/r1f_sweep_compress_paired_copyout.txt)
                 const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
-                for (uint32_t s0 = 0; s0 < n; s0 += 128) {
-                    #pragma unroll
-                    for (uint32_t t = 0; t < 4; ++t) {
-                        const uint32_t s = s0 + t * 32 + lane;
-                        if (s < n)
-                            dst[s] = idx_row + lds_u16(stg_addr + 2 * s);
+                {   // (pointers and the remaining count are stepped explicitly: immediates only inside)
+                    uint32_t *o = dst + lane;
+                    uint32_t sa = stg_addr + 2 * lane;
+                    int32_t rem = (int32_t) n - (int32_t) lane;             // slots left for this lane: rem > 32 t
+                    int32_t left = (int32_t) n;                              // slots left for the warp (uniform)
+                    for (; left > 96; left -= 128, rem -= 128, o += 128, sa += 256) {
+                        #pragma unroll
+                        for (uint32_t t = 0; t < 4; ++t)
+                            if (rem > (int32_t) (t * 32))
+                                o[t * 32] = idx_row + lds_u16(sa + t * 64);
                     }
+                    for (; left > 0; left -= 32, rem -= 32, o += 32, sa += 64)   // short tail: 32 slots per round
+                        if (rem > 0)
+                            *o = idx_row + lds_u16(sa);
                 }
                 __syncwarp();
                 dst += n;
