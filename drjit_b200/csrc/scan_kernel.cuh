@@ -279,6 +279,8 @@ prefix_reduce_kernel(const PrefixParams p) {
         #pragma unroll
         for (uint32_t r = 0; r < ROWS; ++r) {
             const uint32_t u = (warp * ROWS + r) * 32 + lane;       // unit in scan order
+            if (SEG && (u + 1) * V <= first)
+                continue;                                           // entirely before the tile's last head
             Vec16<T> v;
             *reinterpret_cast<uint4 *>(&v) = lds128(src + (SEG && rev ? Geom::TILE_BYTES - (u + 1) * 16 : u * 16));
             #pragma unroll
@@ -375,6 +377,13 @@ prefix_reduce_kernel(const PrefixParams p) {
             }
         }
 
+        uint32_t res = 0, row_step = 0;     // SEG: residue bookkeeping of this thread's units
+        if constexpr (SEG) {
+            const uint64_t first = tile_base + (uint64_t) ((warp * ROWS * 32 + lane) * V);
+            if (first < size)
+                res = rev ? mod_bs((uint64_t) size - first) : mod_bs(first);
+            row_step = mod_bs(32 * V);
+        }
         #pragma unroll
         for (uint32_t k = 0; k < ROWS; ++k) {
             const uint64_t s0 = tile_base + (uint64_t) (((warp * ROWS + k) * 32 + lane) * V);
@@ -402,16 +411,24 @@ prefix_reduce_kernel(const PrefixParams p) {
 
             uint32_t hm = 0;
             if constexpr (SEG) {
+                // forward: head iff i % bs == 0; reverse: head iff (i + 1) % bs == 0, i = size-1-s.
+                // `res` is the residue of the unit's first element (stepped from row to row).
                 if (s0 < size) {
-                    // forward: head iff i % bs == 0; reverse: head iff (i + 1) % bs == 0, i = size-1-s
-                    uint32_t r = rev ? mod_bs((uint64_t) size - s0) : mod_bs(s0);
-                    #pragma unroll
-                    for (uint32_t e = 0; e < V; ++e) {
-                        hm |= (r == 0 ? 1u : 0u) << e;
-                        if (rev) r = r == 0 ? bs - 1 : r - 1;
-                        else     r = r + 1 == bs ? 0 : r + 1;
+                    if (bs >= V) {          // at most one head per unit
+                        const uint32_t d = rev ? res : (res == 0 ? 0u : bs - res);
+                        hm = d < V ? 1u << d : 0u;
+                    } else {
+                        uint32_t r = res;
+                        #pragma unroll
+                        for (uint32_t e = 0; e < V; ++e) {
+                            hm |= (r == 0 ? 1u : 0u) << e;
+                            if (rev) r = r == 0 ? bs - 1 : r - 1;
+                            else     r = r + 1 == bs ? 0 : r + 1;
+                        }
                     }
                 }
+                if (rev) res = res >= row_step ? res - row_step : res + bs - row_step;
+                else     { res += row_step; if (res >= bs) res -= bs; }
             }
             head_mask[k] = hm;
 
