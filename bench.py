@@ -377,6 +377,25 @@ def main():
                             "Gelem_per_s": round(world * size[name] / (ms * 1e-3) / 1e9, 2),
                             "frac_of_peak_per_gpu": round(gbs / (peak * world), 4)}
 
+    # ---- informational (NOT part of `value`): the sharded scan in shard-offset form (8 B/element:
+    # local scan + offset per shard, dist.py) next to the materialised form timed above (12 B/element)
+    if world > 1:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sh.prefix_reduce_offsets(ReduceOp.Add, u, vt=VarType.UInt32, out=u_out)
+        barrier()
+        a.record()
+        for _ in range(args.steps):
+            sh.prefix_reduce_offsets(ReduceOp.Add, u, vt=VarType.UInt32, out=u_out)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        gbs = world * size["prefix_sum_u32"] * 8.0 / (ms * 1e-3) / 1e9
+        primitives["prefix_sum_u32"]["shard_offset_form"] = {
+            "ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_peak_per_gpu": round(gbs / (peak * world), 4),
+            "note": "local scan + per-shard offset (not materialised); informational, not in `value`"}
+
     # ---- end-to-end: host buffers through the public API, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:

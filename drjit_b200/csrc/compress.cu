@@ -36,12 +36,18 @@ static void launch_compress(cudaStream_t stream, CompressParams &p, Scratch &scr
     p.tiles = ceil_div(p.size, TILE);
     const size_t state_bytes = (size_t) p.tiles * 8;
     p.state = (uint64_t *) scratch.device(state_bytes);
-    DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
+    if (p.tiles > 1)        // (a single tile never reads a descriptor)
+        DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 
-    // Cooperative launch: all CTAs co-resident (static tile schedule, see scan_kernel.cuh)
     const uint32_t grid = std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kCompWindowLoads * kCompThreads);
-    void *args[] = { (void *) &p };
-    DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(kCompThreads), args, smem, stream));
+    if (grid == p.tiles) {
+        // one tile per CTA: ordinary launch (see prefix_reduce.cu)
+        kernel<<<grid, kCompThreads, smem, stream>>>(p);
+    } else {
+        // Cooperative launch: all CTAs co-resident (static tile schedule, see scan_kernel.cuh)
+        void *args[] = { (void *) &p };
+        DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(kCompThreads), args, smem, stream));
+    }
     DJB_POST_LAUNCH();
 }
 

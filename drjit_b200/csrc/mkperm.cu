@@ -756,12 +756,16 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     uint32_t warps = 32;
     const uint32_t smem_budget = dev.smem_optin - 1024;
     const MkpermMode mode = pick_mode(bucket_count, smem_budget, warps);
+    // Keys per row (= per warp): a row costs `bucket_count` counters to publish and scan, so it
+    // should see a few times that many keys, but rows are walked 32 keys per match.any step, so
+    // with few buckets shorter rows (more warps and CTAs) cut the latency of mid-sized inputs
+    // (2^16 keys, 64 buckets: 81 -> ~25 us, scripts/small_sizes.py)
+    const uint32_t min_row_elems = std::max(512u, std::min(2048u, 4 * bucket_count));
     // small sorting groups: do not spend more warps (= histogram rows) than the group can feed
-    warps = std::max(1u, std::min(warps, ceil_div(block_size, 2048)));
+    warps = std::max(1u, std::min(warps, ceil_div(block_size, min_row_elems)));
     const uint32_t threads = warps * 32;
 
     // Rows: one per warp. Spread each group over enough CTAs to fill the machine once.
-    const uint32_t min_row_elems = 2048;
     uint32_t ctas_per_group = std::max(1u, dev.sm_count / p.n_groups);
     const uint32_t max_ctas = ceil_div(block_size, min_row_elems * warps);
     ctas_per_group = std::max(1u, std::min(ctas_per_group, max_ctas));

@@ -45,13 +45,21 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     Scratch scratch(stream);
     const size_t state_bytes = TileState<A>::bytes(p.tiles);
     p.state = scratch.device(state_bytes);
-    DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
+    if (p.tiles > 1)        // (a single tile never reads a descriptor)
+        DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 
-    // Cooperative launch: all CTAs are co-resident, which the static tile schedule relies on
     // (the windowed carry reads one descriptor per CTA of the grid with <= kScanWindowLoads loads per thread)
     const uint32_t grid = std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kScanWindowLoads * kScanThreads);
-    void *args[] = { (void *) &p };
-    DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(threads), args, smem, stream));
+    if (grid == p.tiles) {
+        // One tile per CTA: a CTA only ever waits for tiles of lower-numbered CTAs, which were
+        // dispatched before it, so an ordinary launch cannot deadlock (and is ~1 us cheaper)
+        kernel<<<grid, threads, smem, stream>>>(p);
+    } else {
+        // Cooperative launch: all CTAs are co-resident, which the static tile schedule relies on
+        // (a CTA's window includes tiles that higher-numbered CTAs handled one iteration earlier)
+        void *args[] = { (void *) &p };
+        DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(threads), args, smem, stream));
+    }
     DJB_POST_LAUNCH();
 }
 

@@ -77,6 +77,24 @@ class Sharded:
     def prefix_sum(self, x, exclusive=True, vt=None, out=None):
         return self.prefix_reduce(ReduceOp.Add, x, exclusive, vt, out)
 
+    def prefix_reduce_offsets(self, op, x, exclusive=True, vt=None, out=None):
+        """Global prefix reduction in *shard-offset form*: returns ``(local, offset)`` where ``local``
+        is the prefix reduction of this rank's shard alone and ``offset`` (1-element device tensor)
+        the reduction of all lower shards, i.e. global[i] = op(offset, local[i]). This is the form
+        the compress / mkperm offsets take as well: one pass over the shard (read + write, the
+        shard total falls out of the same kernel), then an all-gather of W totals and a W-element
+        exclusive scan. A consumer folds ``offset`` into whatever it does with the values; the
+        materialised form (``prefix_reduce``) costs one more read pass over the shard."""
+        total = torch.empty(1, dtype=x.dtype, device=x.device)
+        local = self.local.prefix_reduce_carry(op, x, exclusive, False, carry_in=None, total_out=total,
+                                               vt=vt, out=out)
+        if self.world == 1:
+            ident = self.local.block_prefix_reduce(op, total, 1, True, False, vt=vt)   # exclusive scan of 1 = identity
+            return local, ident
+        totals = self._all_gather(total)
+        carries = self.local.block_prefix_reduce(op, totals, totals.numel(), True, False, vt=vt)
+        return local, carries[self.rank:self.rank + 1]
+
     # ------------------------------------------------------------------ compress
     def compress(self, mask, index_base, out=None):
         """Shard-local compaction with global indices. Returns (out, counts): rank r owns

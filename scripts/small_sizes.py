@@ -53,6 +53,7 @@ def main():
         B = 64
         off_o = torch.empty(4 * B + 1, dtype=torch.int32).pin_memory()
         off_r = L.ref_malloc(ref.CUDA, 4 * (4 * B + 1), 1) if have_ref else None
+        cnt = ctypes.c_uint32(0)
 
         cases = [
             ("sum u32", 200,
@@ -63,10 +64,11 @@ def main():
              lambda: check(lib.drjit_b200_block_prefix_reduce(stream, VT["u32"], OP["add"], n, n, 1, 0, vp(x.data_ptr()), vp(out.data_ptr())))),
             ("compress (sync)", 50,
              lambda: L.ref_compress(ref.CUDA, vp(m.data_ptr()), n, vp(out.data_ptr())),
-             lambda: dr.compress(m)),
+             lambda: check(lib.drjit_b200_compress(stream, vp(m.data_ptr()), n, vp(out.data_ptr()), ctypes.byref(cnt)))),
             ("mkperm 64 + table", 50,
              lambda: L.ref_block_mkperm(ref.CUDA, vp(keys.data_ptr()), n, n, B, vp(out.data_ptr()), vp(off_r)),
-             lambda: dr.block_mkperm(keys, n, B)),
+             lambda: check(lib.drjit_b200_block_mkperm(stream, vp(keys.data_ptr()), n, n, B, vp(out.data_ptr()),
+                                                       vp(off_o.data_ptr()), ctypes.byref(cnt)))),
         ]
         for name, calls, f_ref, f_ours in cases:
             t_ref = per_call(f_ref, L.ref_sync, calls) if have_ref else float("nan")

@@ -50,6 +50,11 @@ class OracleLocal:
         res = capi.block_prefix_reduce(t, _OPN[int(op)], a, a.size, exclusive, reverse)
         if carry_in is not None:
             res = (res + self._np(carry_in)[1][0]).astype(res.dtype)   # Add only (what the tests use)
+        if total_out is not None:
+            tot = capi.block_reduce(t, _OPN[int(op)], a, a.size)
+            if carry_in is not None:
+                tot = (tot + self._np(carry_in)[1][0]).astype(tot.dtype)
+            total_out.copy_(self._t(tot, x))
         return self._t(res, x)
 
     def compress_async(self, mask, index_base=0, out=None, count=None):
@@ -92,6 +97,10 @@ def _worker(rank, world, port, n):
         got = sh.prefix_sum(ut).numpy().view(np.uint32)
         exp = capi.block_prefix_reduce("u32", "add", u, n, True, False)[lo:hi]
         assert np.array_equal(got, exp)
+
+        # shard-offset form: offset (+) local == the same slice
+        local, off = sh.prefix_reduce_offsets(ReduceOp.Add, ut)
+        assert np.array_equal((local.numpy().view(np.uint32) + off.numpy().view(np.uint32)[0]).astype(np.uint32), exp)
 
         # compress: global indices, rank-order concatenation == oracle list
         m = capi.mask_u8(n, 128)

@@ -42,6 +42,10 @@ def _worker(rank, world, port, n):
         got = sh.prefix_sum(ut, vt=VarType.UInt32).cpu().numpy().view(np.uint32)
         assert np.array_equal(got, capi.block_prefix_reduce("u32", "add", u, n, True, False)[lo:hi])
 
+        local, off = sh.prefix_reduce_offsets(ReduceOp.Add, ut, vt=VarType.UInt32)
+        got = (local.cpu().numpy().view(np.uint32) + off.cpu().numpy().view(np.uint32)[0]).astype(np.uint32)
+        assert np.array_equal(got, capi.block_prefix_reduce("u32", "add", u, n, True, False)[lo:hi])
+
         m = capi.mask_u8(n, 128)
         out, counts = sh.compress(torch.from_numpy(m[lo:hi].copy()).to(dev), lo)
         exp_all = capi.compress(m)
