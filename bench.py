@@ -220,7 +220,8 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200,
+                    help="timed steps (default 200: ~1 s, long enough for nvidia-smi to sample the clocks inside the timed region)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=0, help="shrink every array by 2^SCALE (debug)")
@@ -332,12 +333,12 @@ def main():
     barrier()
     t_load = time.monotonic()
     # W warm-up steps, padded (same count on every rank) so that the clocks are sampled under
-    # this load for >= 0.5 s before the timed region starts
+    # this load for >= 1 s before the timed region starts
     for _ in range(args.warmup):
         one_step()
     barrier()
     elapsed = time.monotonic() - t_load
-    extra = 0 if elapsed >= 0.5 else min(2000, int((0.5 - elapsed) / max(elapsed / args.warmup, 1e-4)) + 1)
+    extra = 0 if elapsed >= 1.0 else min(2000, int((1.0 - elapsed) / max(elapsed / args.warmup, 1e-4)) + 1)
     if world > 1:
         t = torch.tensor([extra], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -458,8 +459,8 @@ def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, p
     # uploads. Every input is still copied host->device and every result device->host in every step.
     fn = dict(prims)
     plan = [  # (primitive, inputs it needs uploaded, outputs to download)
-        ("prefix_sum_u32", ["u"], ["u_out"]),
-        ("compress_u8", ["mask"], ["c_out"]),
+        ("compress_u8", ["mask"], ["c_out"]),          # 1 GB up, 2 GB down: its download overlaps the next upload
+        ("prefix_sum_u32", ["u"], ["u_out"]),         # 4 GB up, 4 GB down
         ("sum_f32", ["x"], []),
         ("block_reduce256_f32", [], ["br_out"]),
         ("dot_f32", ["y"], []),

@@ -16,7 +16,7 @@ for T in 128 3 253; do timeout 60 build/sweep_compress 30 $T > $OUT/sweep_compre
 stamp smoke; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.log
 stamp pytest; timeout 900 python -m pytest tests -q -m gpu --maxfail=20 > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest.log | head -30
 stamp prims; timeout 300 python scripts/time_prims.py all > $OUT/prims.log 2>&1; cat $OUT/prims.log
-stamp bench; timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 4500 $OUT/bench.json; tail -5 $OUT/bench.err
+stamp bench; timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 4500 $OUT/bench.json; tail -5 $OUT/bench.err
 stamp bench-ref; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"; tail -c 600 $OUT/bench_ref.json; tail -5 $OUT/bench_ref.err
 stamp ncu-launches; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_bench.log 2>&1; echo "ncu rc=$?"
 K='regex:reduce|compress|mkperm|scatter'
