@@ -564,6 +564,137 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 }
 
 // ---------------------------------------------------------------------------
+//  Stable tile scatter (bucket counts for which the reference guarantees a stable permutation)
+// ---------------------------------------------------------------------------
+//  jit.h:2404-2406: the reference's "tiny" variant -- bucket_count * 4 bytes * 32 warps fit into
+//  shared memory, i.e. up to 1816 buckets on this GPU -- produces a *stable* permutation, and
+//  dr.sort / dr.argsort rely on it: they are LSD radix sorts made of block_mkperm passes with 256
+//  buckets (drjit/__init__.py:1698-1772). For these bucket counts the tile path therefore ranks
+//  keys in input order: every warp owns a contiguous segment of the tile and walks it 32
+//  consecutive keys at a time; lanes holding the same key are found with one ballot per key bit
+//  (2 instructions per bit instead of a ~64-cycle match.any), the rank inside the step is a
+//  popcount, and the running position of (warp, bucket) lives in a warp-private counter row.
+//  Order inside a bucket = tile order (tile_off) > warp order (column prefix over the per-warp
+//  histograms) > step order > lane order = input order. Everything else (K1, K2, copy-out, L2
+//  prefetch) is shared with the unordered kernel above.
+template <uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+mkperm_tile_scatter_stable_kernel(const MkpermTileParams p, uint32_t key_bits) {
+    constexpr uint32_t TILE = THREADS * kTileKeysPerThread, WARPS = THREADS / 32, SEG = TILE / WARPS;
+    static_assert(TILE <= 65536, "local indices are packed into 16 bits");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t S = p.stride;
+    uint32_t *whist = smem;                    // [WARPS][S] per-warp counts -> running tile-local positions
+    uint32_t *delta = smem + WARPS * S;        // [S] final position of the bucket's run minus its local start
+    uint32_t *sorted = delta + S;              // [TILE] (bucket << 16 | local index), ordered by bucket
+    __shared__ uint32_t warp_sum[WARPS];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, last = p.bucket_count - 1;
+    uint32_t *mine = whist + warp * S;
+
+    for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
+
+        // keys of step s of this warp's segment: seg + s * 32 + lane (coalesced, input order)
+        uint32_t key[kTileKeysPerThread];
+        #pragma unroll
+        for (uint32_t s = 0; s < kTileKeysPerThread; ++s) {
+            const uint32_t i = warp * SEG + s * 32 + lane;
+            key[s] = i < n_tile ? min(__ldg(p.values + tile_base + i), last) : 0xffffffffu;
+        }
+        if (tid == 0) {
+            const uint64_t next = (uint64_t) tile + gridDim.x;
+            if (next < p.tiles) {
+                if (p.vec && (next + 1) * TILE <= p.size)
+                    bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
+                bulk_prefetch_l2(p.tile_off + next * S, S * 4);
+            }
+        }
+
+        // ---- (1) per-warp histograms of the segments -------------------------------------------
+        for (uint32_t b = lane; b < S; b += 32) mine[b] = 0;
+        __syncwarp();
+        #pragma unroll
+        for (uint32_t s = 0; s < kTileKeysPerThread; ++s)
+            if (key[s] != 0xffffffffu) atomicAdd(mine + key[s], 1u);
+        __syncthreads();
+
+        // ---- (2) bins: prefix over the warps of each bucket, then over the buckets ----------------
+        {
+            const uint32_t chunk = tile / p.tiles_per_chunk;
+            const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < S; base += THREADS) {
+                const uint32_t b = base + tid;
+                uint32_t tot = 0, goff = 0;
+                if (b < S) {
+                    goff = __ldg(toff + b) + __ldg(crow + b);
+                    #pragma unroll 8
+                    for (uint32_t w = 0; w < WARPS; ++w) {
+                        const uint32_t c = whist[w * S + b];
+                        whist[w * S + b] = tot;
+                        tot += c;
+                    }
+                }
+                uint32_t incl = tot;
+                #pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = shfl_up(incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) warp_sum[warp] = incl;
+                __syncthreads();
+                uint32_t wbase = 0, total = 0;
+                #pragma unroll
+                for (uint32_t w = 0; w < WARPS; ++w) {
+                    if (w == warp) wbase = total;
+                    total += warp_sum[w];
+                }
+                const uint32_t start = carry + wbase + incl - tot;      // tile-local start of bucket b
+                carry += total;
+                if (b < S) {
+                    #pragma unroll 8
+                    for (uint32_t w = 0; w < WARPS; ++w) whist[w * S + b] += start;
+                    delta[b] = goff - start;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- (3) ranking walk in input order -------------------------------------------------------
+        #pragma unroll
+        for (uint32_t s = 0; s < kTileKeysPerThread; ++s) {
+            const uint32_t k = key[s];
+            const bool valid = k != 0xffffffffu;
+            uint32_t peers = __ballot_sync(kFullMask, valid);
+            if (peers == 0) break;                                   // (ragged last tile)
+            for (uint32_t bit = 0; bit < key_bits; ++bit) {
+                const bool one = (k >> bit) & 1u;
+                const uint32_t v = __ballot_sync(kFullMask, one);
+                peers &= one ? v : ~v;
+            }
+            const uint32_t rank = __popc(peers & lanemask_lt());
+            uint32_t pos = 0;
+            if (valid) pos = mine[k] + rank;
+            __syncwarp();
+            if (valid && rank == 0) mine[k] = pos + __popc(peers);  // lowest lane of the group
+            __syncwarp();
+            if (valid) sorted[pos] = (k << 16) | (warp * SEG + s * 32 + lane);
+        }
+        __syncthreads();
+
+        // ---- (4) runs of equal buckets are contiguous in `sorted` and in `perm` --------------------
+        const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
+        #pragma unroll 4
+        for (uint32_t j = tid; j < n_tile; j += THREADS) {
+            const uint32_t e = sorted[j];
+            p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 //  Host side
 // ---------------------------------------------------------------------------
 static MkpermMode pick_mode(uint32_t bucket_count, uint32_t smem_budget, uint32_t &warps) {
@@ -621,8 +752,7 @@ static cudaEvent_t mkperm_event() {
     return ev;
 }
 
-/// Developer overrides for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path,
-/// DRJIT_B200_MKPERM_TILE_KEYS=16|32 picks the tile size (Ki keys)
+/// Developer override for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path
 static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_count) {
     static int enabled = -1;
     if (enabled < 0) {
@@ -634,7 +764,7 @@ static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_coun
            tiles * bucket_count * 6 <= ((uint64_t) 2 << 30);
 }
 
-template <uint32_t THREADS>
+template <uint32_t THREADS, bool STABLE>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
                              uint32_t *offsets, uint32_t *hist_out) {
@@ -648,7 +778,8 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     t.vec = ((uintptr_t) values % 16) == 0;
 
     const uint32_t hist_smem = t.stride * 8,
-                   scatter_smem = t.stride * 8 + TILE * 4;
+                   scatter_smem = STABLE ? (THREADS / 32 + 1) * t.stride * 4 + TILE * 4
+                                         : t.stride * 8 + TILE * 4;
     uint32_t chunks = std::min(t.tiles, dev.sm_count * 2);
     t.tiles_per_chunk = ceil_div(t.tiles, chunks);
     chunks = ceil_div(t.tiles, t.tiles_per_chunk);
@@ -689,8 +820,12 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     if (!configured) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));
-        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int) (kTileMaxBuckets * 8 + TILE * 4)));
+        if (STABLE)
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_stable_kernel<THREADS>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dev.smem_optin - 1024));   // (static part: warp_sum)
+        else
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int) (kTileMaxBuckets * 8 + TILE * 4)));
         configured = true;
     }
 
@@ -707,9 +842,16 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     mkperm_fold_starts_kernel<<<dim3(ceil_div(bucket_count, 256), std::min(chunks, 32u)), 256, 0, stream>>>(
         t.rows, t.bucket_start, chunks, bucket_count, t.stride);
     DJB_POST_LAUNCH();
-    const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
-    const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
-    mkperm_tile_scatter_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t);
+    if (STABLE) {
+        uint32_t key_bits = 0;
+        while ((1u << key_bits) < bucket_count) ++key_bits;
+        const uint32_t grid = std::min(t.tiles, dev.sm_count);
+        mkperm_tile_scatter_stable_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t, key_bits);
+    } else {
+        const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
+        const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
+        mkperm_tile_scatter_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t);
+    }
     DJB_POST_LAUNCH();
 
     if (!want_table)
@@ -739,18 +881,21 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.n_groups = ceil_div(size, block_size);
 
     if (use_tile_path(p.n_groups, size, bucket_count)) {
-        // 32 Ki-key tiles (1 CTA/SM) double the length of the runs written per bucket and win when
-        // there are many buckets; 16 Ki-key tiles (2 CTAs/SM) overlap better and win for few
-        // (measured at 2^26 keys: 4096 buckets 0.352 vs 0.520 ms, 256 buckets 0.243 vs 0.227 ms)
-        static int tile_ki = -1;
-        if (tile_ki < 0) {
-            const char *env = getenv("DRJIT_B200_MKPERM_TILE_KEYS");
-            tile_ki = env ? atoi(env) : 0;
+        // Where the reference's "tiny" variant applies (bucket_count * 4 B * 32 warps fit into shared
+        // memory, jit.h:2404-2406, cuda_ts.cpp:824-836) its permutation is stable and dr.sort depends
+        // on that, so is ours; beyond it the reference is unordered as well and the faster unordered
+        // tile kernel is used. DRJIT_B200_MKPERM_UNORDERED=1 forces the latter (A/B measurements only).
+        static int force_unordered = -1;
+        if (force_unordered < 0) {
+            const char *env = getenv("DRJIT_B200_MKPERM_UNORDERED");
+            force_unordered = env ? atoi(env) != 0 : 0;
         }
-        const bool big = tile_ki ? tile_ki == 32 : bucket_count >= 1024;
-        if (big)
-            return mkperm_tiles<1024>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
-        return mkperm_tiles<512>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        const bool stable = (uint64_t) bucket_count * 4 * 32 <= dev.smem_optin && !force_unordered;
+        if (stable && bucket_count <= 512)      // 32 per-warp counter rows + a 32 Ki-key tile fit
+            return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        if (stable)                             // 16 rows + a 16 Ki-key tile (up to 1816 buckets)
+            return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
     }
 
     uint32_t warps = 32;

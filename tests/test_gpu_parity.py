@@ -443,6 +443,41 @@ def test_mkperm_stable_variant_is_bit_exact():
                 assert digest(to_np(perm, "u32"))[0] == digests[f"mkperm_block/{n}/{buckets}/{bs}"], (n, buckets, bs)
 
 
+@pytest.mark.parametrize("buckets", [1, 2, 37, 256, 512, 513, 1000, 1816])
+@pytest.mark.parametrize("n", [(1 << 18) + 5, (1 << 21) + 12345])
+def test_mkperm_large_inputs_stay_stable_where_the_reference_is(buckets, n):
+    """jit.h:2404-2406: while bucket_count * 4 B * 32 warps fit into shared memory (<= 1816 buckets
+    here) the reference's permutation is stable; the tile path used for large inputs must
+    reproduce the stable (CPU reference) permutation bit for bit, table included."""
+    keys = capi.fmix32(n) % np.uint32(buckets)
+    if buckets > 2:
+        keys[keys == 1] = 0                      # one empty bucket
+    perm, table = dr.block_mkperm(to_dev(keys, "u32"), n, buckets)
+    torch.cuda.synchronize()
+    eperm, eoff, eunique = capi.block_mkperm(keys, n, buckets)
+    assert np.array_equal(to_np(perm, "u32"), eperm)
+    assert table.shape[0] == eunique and np.array_equal(table.numpy().astype(np.uint32).reshape(-1), eoff[:4 * eunique])
+
+
+def test_lsd_radix_sort_on_top_of_block_mkperm():
+    """dr.sort / dr.argsort (drjit/__init__.py:1698-1772): LSD radix sort of 32-bit keys made of
+    four block_mkperm passes with 256 buckets; only correct if every pass is stable."""
+    n = (1 << 20) + 777
+    x = torch.from_numpy(capi.fmix32(n, xor=0x1234567).view(np.int32)).cuda()
+    ordinal = x.to(torch.int64) & 0xFFFFFFFF
+    ordinal[::3] &= 0xFFFF0000                   # plenty of equal keys: the result must be the *stable* order
+    index = torch.arange(n, device="cuda")
+    cur, cur_index = ordinal.clone(), index.clone()
+    for shift in (0, 8, 16, 24):
+        digit = ((cur >> shift) & 0xFF).to(torch.int32)
+        perm, _ = dr.block_mkperm(digit, n, 256, want_offsets=False)
+        torch.cuda.synchronize()
+        pl = perm.to(torch.int64)
+        cur, cur_index = cur[pl], cur_index[pl]
+    exp_sorted, exp_index = torch.sort(ordinal, stable=True)
+    assert torch.equal(cur, exp_sorted) and torch.equal(cur_index, exp_index)
+
+
 @pytest.mark.parametrize("buckets", [1, 2, 37, 256, 4096, 8000, 50000, 100000])
 def test_mkperm_variants(buckets):
     """per-warp (stable), per-CTA and global-atomic variants; single group and sorting groups"""
