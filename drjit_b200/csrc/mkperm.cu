@@ -30,6 +30,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace djb {
 
@@ -577,9 +578,9 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 //  Order inside a bucket = tile order (tile_off) > warp order (column prefix over the per-warp
 //  histograms) > step order > lane order = input order. Everything else (K1, K2, copy-out, L2
 //  prefetch) is shared with the unordered kernel above.
-template <uint32_t THREADS>
+template <uint32_t THREADS, uint32_t KEY_BITS>
 __global__ void __launch_bounds__(THREADS, 1)
-mkperm_tile_scatter_stable_kernel(const MkpermTileParams p, uint32_t key_bits) {
+mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
     constexpr uint32_t TILE = THREADS * kTileKeysPerThread, WARPS = THREADS / 32, SEG = TILE / WARPS;
     static_assert(TILE <= 65536, "local indices are packed into 16 bits");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -662,25 +663,31 @@ mkperm_tile_scatter_stable_kernel(const MkpermTileParams p, uint32_t key_bits) {
         }
 
         // ---- (3) ranking walk in input order -------------------------------------------------------
-        #pragma unroll
-        for (uint32_t s = 0; s < kTileKeysPerThread; ++s) {
-            const uint32_t k = key[s];
-            const bool valid = k != 0xffffffffu;
-            uint32_t peers = __ballot_sync(kFullMask, valid);
-            if (peers == 0) break;                                   // (ragged last tile)
-            for (uint32_t bit = 0; bit < key_bits; ++bit) {
-                const bool one = (k >> bit) & 1u;
-                const uint32_t v = __ballot_sync(kFullMask, one);
-                peers &= one ? v : ~v;
+        // (FULL: every lane holds a key; only the last tile of the array can be ragged)
+        auto walk = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            #pragma unroll
+            for (uint32_t s = 0; s < kTileKeysPerThread; ++s) {
+                const uint32_t k = key[s];
+                const bool valid = FULL || k != 0xffffffffu;
+                uint32_t peers = FULL ? kFullMask : __ballot_sync(kFullMask, valid);
+                #pragma unroll
+                for (uint32_t bit = 0; bit < KEY_BITS; ++bit) {
+                    const bool one = k & (1u << bit);
+                    const uint32_t v = __ballot_sync(kFullMask, one);
+                    peers &= one ? v : ~v;
+                }
+                const uint32_t rank = __popc(peers & lanemask_lt());
+                uint32_t pos = 0;
+                if (valid) pos = mine[k] + rank;
+                __syncwarp();
+                if (valid && rank == 0) mine[k] = pos + __popc(peers);  // lowest lane of the group
+                __syncwarp();
+                if (valid) sorted[pos] = (k << 16) | (warp * SEG + s * 32 + lane);
             }
-            const uint32_t rank = __popc(peers & lanemask_lt());
-            uint32_t pos = 0;
-            if (valid) pos = mine[k] + rank;
-            __syncwarp();
-            if (valid && rank == 0) mine[k] = pos + __popc(peers);  // lowest lane of the group
-            __syncwarp();
-            if (valid) sorted[pos] = (k << 16) | (warp * SEG + s * 32 + lane);
-        }
+        };
+        if (n_tile == TILE) walk(std::true_type{});
+        else                walk(std::false_type{});
         __syncthreads();
 
         // ---- (4) runs of equal buckets are contiguous in `sorted` and in `perm` --------------------
@@ -764,6 +771,17 @@ static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_coun
            tiles * bucket_count * 6 <= ((uint64_t) 2 << 30);
 }
 
+template <uint32_t THREADS, uint32_t KEY_BITS>
+static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t, uint32_t grid, uint32_t smem, uint32_t smem_max) {
+    static bool configured = false;
+    if (!configured) {
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max));
+        configured = true;
+    }
+    mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS><<<grid, THREADS, smem, stream>>>(t);
+}
+
 template <uint32_t THREADS, bool STABLE>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
@@ -820,10 +838,7 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     if (!configured) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));
-        if (STABLE)
-            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_stable_kernel<THREADS>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dev.smem_optin - 1024));   // (static part: warp_sum)
-        else
+        if (!STABLE)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int) (kTileMaxBuckets * 8 + TILE * 4)));
         configured = true;
@@ -843,10 +858,12 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
         t.rows, t.bucket_start, chunks, bucket_count, t.stride);
     DJB_POST_LAUNCH();
     if (STABLE) {
-        uint32_t key_bits = 0;
-        while ((1u << key_bits) < bucket_count) ++key_bits;
-        const uint32_t grid = std::min(t.tiles, dev.sm_count);
-        mkperm_tile_scatter_stable_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t, key_bits);
+        // one ballot per key bit, unrolled: instantiated for 4 / 8 / 9 (32 Ki-key tiles) and 11 bits
+        const uint32_t grid = std::min(t.tiles, dev.sm_count), smem_max = dev.smem_optin - 1024;  // (static part: warp_sum)
+        if (THREADS == 512)          launch_stable_scatter<512, 11>(stream, t, grid, scatter_smem, smem_max);
+        else if (bucket_count <= 16)  launch_stable_scatter<1024, 4>(stream, t, grid, scatter_smem, smem_max);
+        else if (bucket_count <= 256) launch_stable_scatter<1024, 8>(stream, t, grid, scatter_smem, smem_max);
+        else                          launch_stable_scatter<1024, 9>(stream, t, grid, scatter_smem, smem_max);
     } else {
         const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
         const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);

@@ -55,6 +55,7 @@ def time_ours(fn, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2-shift", type=int, default=0)
+    ap.add_argument("--buckets", type=int, default=4096, help="bucket count of the block_mkperm row")
     a = ap.parse_args()
     S = a.log2_shift
     L = ref.lib(cuda=True, llvm=False)
@@ -116,7 +117,7 @@ def main():
     del mbuf, m, c_r, cnt
 
     # ---- block_mkperm, 4096 buckets --------------------------------------------------------------------
-    n = 1 << (26 - S); B = 4096
+    n = 1 << (26 - S); B = a.buckets
     keys = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(keys, 0, and_=B - 1)
     perm_r = torch.empty_like(keys)
     off_ptr = L.ref_malloc(ref.CUDA, 4 * (4 * B + 1), 1)             # host-pinned, as the reference requires
@@ -147,7 +148,7 @@ def main():
     verdict = ("identical" if ok_table and ok_sets and grouped_o and grouped_r else
                f"MISMATCH (table {ok_table}, sets {ok_sets}, grouped ours {grouped_o} / reference {grouped_r}; "
                f"4th table word ours {tab_o[:2, 3].tolist()} reference {tab_r[:2, 3].tolist()})")
-    report("block_mkperm 4096 buckets", n, 12, t_ref, t_ours, f"{uniq['r']} buckets, table {{id,start,size}} + per-bucket contents " + verdict)
+    report(f"block_mkperm {B} buckets", n, 12, t_ref, t_ours, f"{uniq['r']} buckets, table {{id,start,size}} + per-bucket contents " + verdict)
     L.ref_free(off_ptr)
     del keys, perm_r, canon_r, canon_o, k64, pr, po
 
