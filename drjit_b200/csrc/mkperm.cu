@@ -45,6 +45,7 @@ struct MkpermParams {
     uint32_t n_groups, ctas_per_group, rows_per_group, row_elems; // row = slice of a group
     uint32_t index_base;
     uint32_t row_stride;     // elements between histogram rows (0: bucket_count)
+    uint32_t key_bits;       // ceil(log2(bucket_count))
     uint8_t vec;
 };
 
@@ -285,11 +286,16 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
             for (int u = 0; u < 4; ++u) {
                 const uint32_t active = __ballot_sync(kFullMask, ok[u]);
                 if (active == 0) break;
-                uint32_t pos = 0, peers = 0;
-                if (ok[u]) {
-                    peers = __match_any_sync(active, key[u]);
-                    pos = ctr[key[u]] + __popc(peers & lanemask_lt());
+                // lanes holding the same key: one ballot per key bit (a match.any occupies a unit
+                // that is shared by the whole SM for ~64 cycles, scripts/microbench.cu)
+                uint32_t pos = 0, peers = active;
+                for (uint32_t bit = 0; bit < p.key_bits; ++bit) {
+                    const bool one = ok[u] && ((key[u] >> bit) & 1u);
+                    const uint32_t v = __ballot_sync(kFullMask, one);
+                    peers &= one ? v : ~v;
                 }
+                if (ok[u])
+                    pos = ctr[key[u]] + __popc(peers & lanemask_lt());
                 __syncwarp();
                 if (ok[u] && (peers & lanemask_lt()) == 0)      // lowest lane of the peer group
                     ctr[key[u]] += __popc(peers);
@@ -896,6 +902,7 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.values = values; p.perm = perm; p.size = size; p.block_size = block_size;
     p.bucket_count = bucket_count; p.index_base = index_base;
     p.n_groups = ceil_div(size, block_size);
+    while ((1u << p.key_bits) < bucket_count) ++p.key_bits;
 
     if (use_tile_path(p.n_groups, size, bucket_count)) {
         // Where the reference's "tiny" variant applies (bucket_count * 4 B * 32 warps fit into shared
