@@ -584,6 +584,15 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 //  Order inside a bucket = tile order (tile_off) > warp order (column prefix over the per-warp
 //  histograms) > step order > lane order = input order. Everything else (K1, K2, copy-out, L2
 //  prefetch) is shared with the unordered kernel above.
+/// peers &= (lanes whose key agrees with mine in the bit `mask`): test, ballot, select, one LOP3
+__device__ __forceinline__ uint32_t match_bit(uint32_t peers, uint32_t key, uint32_t mask) {
+    const bool one = key & mask;
+    const uint32_t v = __ballot_sync(kFullMask, one), kb = one ? 0xffffffffu : 0u;
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x90;" : "=r"(d) : "r"(peers), "r"(v), "r"(kb));    // peers & ~(v ^ kb)
+    return d;
+}
+
 template <uint32_t THREADS, uint32_t KEY_BITS>
 __global__ void __launch_bounds__(THREADS, 1)
 mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
@@ -678,11 +687,8 @@ mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
                 const bool valid = FULL || k != 0xffffffffu;
                 uint32_t peers = FULL ? kFullMask : __ballot_sync(kFullMask, valid);
                 #pragma unroll
-                for (uint32_t bit = 0; bit < KEY_BITS; ++bit) {
-                    const bool one = k & (1u << bit);
-                    const uint32_t v = __ballot_sync(kFullMask, one);
-                    peers &= one ? v : ~v;
-                }
+                for (uint32_t bit = 0; bit < KEY_BITS; ++bit)
+                    peers = match_bit(peers, k, 1u << bit);
                 const uint32_t rank = __popc(peers & lanemask_lt());
                 uint32_t pos = 0;
                 if (valid) pos = mine[k] + rank;
