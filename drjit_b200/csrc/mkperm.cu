@@ -921,7 +921,10 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
             force_unordered = env ? atoi(env) != 0 : 0;
         }
         const bool stable = (uint64_t) bucket_count * 4 * 32 <= dev.smem_optin && !force_unordered;
-        if (stable && bucket_count <= 512)      // 32 per-warp counter rows + a 32 Ki-key tile fit
+        // 32 per-warp counter rows + a 32 Ki-key tile fit up to 512 buckets; inputs that would leave
+        // a quarter of the SMs without such a tile take 16 Ki-key tiles (twice as many CTAs at work:
+        // 2^18..2^21 keys 45 -> 35 us, scripts/small_sizes.py)
+        if (stable && bucket_count <= 512 && size >= dev.sm_count * 24576u)
             return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         if (stable)                             // 16 rows + a 16 Ki-key tile (up to 1816 buckets)
             return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
