@@ -351,8 +351,7 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
 //                        atomics/clk/SM measured); per tile it records the running counts
 //                        before the tile (tile_off, exclusive prefix inside the chunk) and
 //                        the tile's own counts (cnt16).
-//    K2 column scan over the chunk totals + bucket scan (kernels above) + one tiny pass that
-//       folds the bucket starts into the chunk offsets.
+//    K2 column scan over the chunk totals + bucket scan (kernels above).
 //    K3 tile scatter   : per tile: (1) bins: exclusive scan of the tile's counts -> one write
 //                        cursor per bucket in shared memory, plus the distance between a slot of
 //                        the tile-local order and its final position (all 128-bit loads/stores,
@@ -375,7 +374,7 @@ struct MkpermTileParams {
     uint32_t *perm;
     uint32_t *tile_off;      // [tiles][stride] exclusive prefix of the tile inside its chunk
     uint16_t *tile_cnt;      // [tiles][stride] counts of the tile
-    uint32_t *rows;          // [chunks][stride] chunk totals -> exclusive chunk offsets (+ bucket starts)
+    uint32_t *rows;          // [chunks][stride] chunk totals -> exclusive chunk offsets
     const uint32_t *bucket_start; // [buckets] after the bucket scan
     uint32_t size, bucket_count, stride, tiles, tiles_per_chunk, index_base;
     uint8_t vec;
@@ -452,17 +451,6 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
     for (uint32_t b = tid; b < S; b += THREADS) row[b] = hist[b];
 }
 
-/// rows[c][b] += bucket_start[b]: after this, rows[c][b] + tile_off[t][b] is the final position
-/// of the first key of bucket b in tile t (t in chunk c)
-__global__ void mkperm_fold_starts_kernel(uint32_t *rows, const uint32_t *bucket_start, uint32_t chunks,
-                                          uint32_t buckets, uint32_t stride) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= buckets) return;
-    const uint32_t s = bucket_start[b];
-    for (uint32_t c = blockIdx.y; c < chunks; c += gridDim.y)
-        rows[(size_t) c * stride + b] += s;
-}
-
 template <uint32_t THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_scatter_kernel(const MkpermTileParams p) {
@@ -512,10 +500,13 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
                                 t1 = __ldg(reinterpret_cast<const uint4 *>(toff + b0 + 4)),
                                 r0 = __ldg(reinterpret_cast<const uint4 *>(crow + b0)),
                                 r1 = __ldg(reinterpret_cast<const uint4 *>(crow + b0 + 4));
+                    uint32_t s8[8];     // bucket starts (the array has bucket_count entries: no vector loads past it)
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) s8[j] = b0 + j < p.bucket_count ? __ldg(p.bucket_start + b0 + j) : 0u;
                     c[0] = cc.x & 0xffffu; c[1] = cc.x >> 16; c[2] = cc.y & 0xffffu; c[3] = cc.y >> 16;
                     c[4] = cc.z & 0xffffu; c[5] = cc.z >> 16; c[6] = cc.w & 0xffffu; c[7] = cc.w >> 16;
-                    g[0] = t0.x + r0.x; g[1] = t0.y + r0.y; g[2] = t0.z + r0.z; g[3] = t0.w + r0.w;
-                    g[4] = t1.x + r1.x; g[5] = t1.y + r1.y; g[6] = t1.z + r1.z; g[7] = t1.w + r1.w;
+                    g[0] = t0.x + r0.x + s8[0]; g[1] = t0.y + r0.y + s8[1]; g[2] = t0.z + r0.z + s8[2]; g[3] = t0.w + r0.w + s8[3];
+                    g[4] = t1.x + r1.x + s8[4]; g[5] = t1.y + r1.y + s8[5]; g[6] = t1.z + r1.z + s8[6]; g[7] = t1.w + r1.w + s8[7];
                 }
                 uint32_t sum = 0;
                 #pragma unroll
@@ -644,7 +635,7 @@ mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
                 const uint32_t b = base + tid;
                 uint32_t tot = 0, goff = 0;
                 if (b < S) {
-                    goff = __ldg(toff + b) + __ldg(crow + b);
+                    goff = __ldg(toff + b) + __ldg(crow + b) + (b < p.bucket_count ? __ldg(p.bucket_start + b) : 0u);
                     #pragma unroll 8
                     for (uint32_t w = 0; w < WARPS; ++w) {
                         const uint32_t c = whist[w * S + b];
@@ -866,9 +857,6 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     cudaEvent_t ev = want_table ? mkperm_event() : nullptr;
     if (ev)
         DJB_CUDA_CHECK(cudaEventRecord(ev, stream));       // cuda_ts.cpp:953 (before the scatter pass)
-    mkperm_fold_starts_kernel<<<dim3(ceil_div(bucket_count, 256), std::min(chunks, 32u)), 256, 0, stream>>>(
-        t.rows, t.bucket_start, chunks, bucket_count, t.stride);
-    DJB_POST_LAUNCH();
     if (STABLE) {
         // one ballot per key bit, unrolled: instantiated for 4 / 8 / 9 (32 Ki-key tiles) and 11 bits
         const uint32_t grid = std::min(t.tiles, dev.sm_count), smem_max = dev.smem_optin - 1024;  // (static part: warp_sum)
