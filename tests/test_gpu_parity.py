@@ -94,6 +94,25 @@ def test_block_reduce_float_ops(vt, op):
                 assert_close(got, exp, vt, bs, f"{vt} {op} size={size} bs={bs}")
 
 
+@pytest.mark.parametrize("vt", ["u8", "f16", "i32", "u32", "f32", "u64", "f64"])
+def test_block_reduce_tiny_blocks(vt):
+    """block sizes that fill a 16-byte vector or an integer fraction of one (dedicated kernel):
+    every op of the type, whole-vector and ragged sizes, aligned and offset input"""
+    ops_for = ["add", "mul", "min", "max"] + ([] if vt[0] == "f" else ["and", "or"])
+    for size in [64, 4096 * 3, (1 << 20) + 16, (1 << 20) + 5]:
+        x = make_input(vt, size)
+        for misalign in (0, 1):
+            xd = to_dev(x, vt, misalign)
+            for bs in (2, 4, 8, 16):
+                for op in ops_for:
+                    got = to_np(dr.block_reduce(OPS[op], xd, bs, vt=VT[vt]), vt)
+                    exp = capi.block_reduce(vt, op, x, bs, acc64=(vt[0] == "f"))
+                    if vt[0] == "f" and op in ("add", "mul"):
+                        assert_close(got, exp, vt, bs, f"{vt} {op} bs={bs} size={size}")
+                    else:
+                        assert np.array_equal(got, exp), (vt, op, bs, size, misalign)
+
+
 def test_block_reduce_golden_fixture():
     """against outputs of the unmodified reference (tests/golden/ref_llvm.npz), integer digests"""
     digests, _ = loader.load()
