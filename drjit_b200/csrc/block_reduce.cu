@@ -205,6 +205,64 @@ static bool try_tiny(cudaStream_t stream, const T *in, T *out, uint32_t size, ui
 }
 
 // ---------------------------------------------------------------------------
+//  Short blocks that do not divide a vector (block_size 3, 5, 6, 7: sums over a short tensor axis)
+// ---------------------------------------------------------------------------
+//  A thread owns V consecutive blocks = BS consecutive 128-bit vectors: BS loads in flight, the
+//  blocks are folded in registers, the V results leave as one 128-bit store. Neighbouring lanes
+//  are BS * 16 bytes apart, so each load instruction touches every sector of the warp's span only
+//  partly; the loads are allowed to allocate in L1 so that the other half of a sector is an L1 hit.
+template <typename T, typename Op, uint32_t BS>
+__global__ void __launch_bounds__(kThreads)
+block_reduce_vecblocks_kernel(const T *__restrict__ in, T *__restrict__ out, uint64_t n_groups) {
+    using A = acc_t<T>;
+    constexpr uint32_t V = 16 / sizeof(T);
+    const uint64_t stride = (uint64_t) gridDim.x * kThreads;
+    for (uint64_t g = (uint64_t) blockIdx.x * kThreads + threadIdx.x; g < n_groups; g += stride) {
+        union { uint4 raw[BS]; T e[BS * V]; } buf;
+        const uint4 *src = reinterpret_cast<const uint4 *>(in) + g * BS;
+        #pragma unroll
+        for (uint32_t k = 0; k < BS; ++k) buf.raw[k] = __ldg(src + k);
+        Vec16<T> res;
+        #pragma unroll
+        for (uint32_t b = 0; b < V; ++b) {
+            A acc = to_acc<A>(buf.e[b * BS]);
+            #pragma unroll
+            for (uint32_t e = 1; e < BS; ++e)
+                acc = Op::template apply<A>(acc, to_acc<A>(buf.e[b * BS + e]));
+            res.v[b] = from_acc<T>(acc);
+        }
+        st_stream<T>(out + g * V, res);
+    }
+}
+
+template <typename T, typename Op, uint32_t BS>
+static uint64_t launch_vecblocks(cudaStream_t stream, const T *in, T *out, uint32_t size) {
+    constexpr uint32_t V = 16 / sizeof(T);
+    const DeviceProps &dev = device_props();
+    const uint64_t n_groups = size / (BS * V);
+    if (n_groups) {
+        const uint32_t grid = (uint32_t) std::min<uint64_t>((n_groups + kThreads - 1) / kThreads, dev.sm_count * 8 * 4);
+        block_reduce_vecblocks_kernel<T, Op, BS><<<grid, kThreads, 0, stream>>>(in, out, n_groups);
+        DJB_POST_LAUNCH();
+    }
+    return n_groups * BS * V;       // elements consumed (a whole number of blocks)
+}
+
+/// Elements taken by the short-block kernel (0: not applicable); the caller reduces the tail
+template <typename T, typename Op>
+static uint64_t try_vecblocks(cudaStream_t stream, const T *in, T *out, uint32_t size, uint32_t block_size) {
+    if (((uintptr_t) in % 16) || ((uintptr_t) out % 16) || size < (1u << 16))
+        return 0;
+    switch (block_size) {
+        case 3: return launch_vecblocks<T, Op, 3>(stream, in, out, size);
+        case 5: return launch_vecblocks<T, Op, 5>(stream, in, out, size);
+        case 6: return launch_vecblocks<T, Op, 6>(stream, in, out, size);
+        case 7: return launch_vecblocks<T, Op, 7>(stream, in, out, size);
+        default: return 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
 //  Chunk kernel (also the dot product when DOT)
 // ---------------------------------------------------------------------------
 template <typename T, typename Op, bool DOT> struct ChunkAccum {
@@ -353,6 +411,16 @@ static void launch_block_reduce(cudaStream_t stream, uint32_t size, uint32_t blo
 
     if (block_bytes <= 16 && try_tiny<T, Op>(stream, in, out, size, block_size))
         return;
+    if (block_size <= 7) {
+        const uint64_t done = try_vecblocks<T, Op>(stream, in, out, size, block_size);
+        if (done == size)
+            return;
+        if (done) {     // fewer than V blocks are left: the general path below takes them
+            launch_block_reduce<T, Op>(stream, (uint32_t) (size - done), std::min<uint32_t>(block_size, (uint32_t) (size - done)),
+                                       in + done, out + done / block_size);
+            return;
+        }
+    }
 
     if (block_bytes <= kGroupMaxBytes) {
         const bool vec = block_size % V == 0 && size % V == 0 && ((uintptr_t) in % 16) == 0;

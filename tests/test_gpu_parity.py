@@ -103,7 +103,7 @@ def test_block_reduce_tiny_blocks(vt):
         x = make_input(vt, size)
         for misalign in (0, 1):
             xd = to_dev(x, vt, misalign)
-            for bs in (2, 4, 8, 16):
+            for bs in (2, 3, 4, 5, 6, 7, 8, 16):      # (3, 5, 6, 7: the short-block kernel + a general-path tail)
                 for op in ops_for:
                     got = to_np(dr.block_reduce(OPS[op], xd, bs, vt=VT[vt]), vt)
                     exp = capi.block_reduce(vt, op, x, bs, acc64=(vt[0] == "f"))
