@@ -1,5 +1,5 @@
 #!/bin/bash
-# Evidence visit: geometry sweeps of the windowed-carry scan / compress, smoke, parity tests,
+# Evidence visit without the `ncu --set full` captures (those reports are ~60 MB: see gpu_evidence.sh):
 # per-primitive timings, both bench arms, ncu launch list of the bench command, and one
 # `ncu --set full` capture per hot kernel.
 TAG=${1:-r1c}
@@ -19,11 +19,5 @@ stamp prims; timeout 300 python scripts/time_prims.py all > $OUT/prims.log 2>&1;
 stamp bench; timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 4500 $OUT/bench.json; tail -5 $OUT/bench.err
 stamp bench-ref; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"; tail -c 600 $OUT/bench_ref.json; tail -5 $OUT/bench_ref.err
 stamp ncu-launches; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_bench.log 2>&1; echo "ncu rc=$?"
-K='regex:reduce|compress|mkperm|scatter'
-for P in scan compress sum block_reduce dot mkperm scatter; do
-  stamp "ncu-full $P"
-  timeout 300 ncu --set full --clock-control none --import-source on -k "$K" -s 1 -c 2 -f -o $OUT/full_$P \
-      python scripts/time_prims.py $P --reps 1 --warm 1 > $OUT/ncu_full_$P.log 2>&1; echo "ncu full $P rc=$?"
-done
 stamp done
 ls -la $OUT
