@@ -180,9 +180,9 @@ compress_kernel(const CompressParams p) {
             st_relaxed_u64(p.state + t, ((uint64_t) c << 32) | kCAggregate);
     };
 
-    // Tiles are decoded (and their counts published) two iterations before they are compacted:
-    // with one iteration of slack the carry windows below were found polling for a fifth of all
-    // issued instructions (profiles/r1c), with two they find everything in place.
+    // Tiles are decoded (and their counts published) two iterations before they are compacted, the
+    // same slack the scan's three-stage ring gives its aggregates: the carry windows below then
+    // find every count in place even when CTAs drift apart by an iteration.
     uint32_t cur[PAIRS], nxt[PAIRS], nxt2[PAIRS];
     uint32_t carry = 0;                 // selected entries in all tiles before the current one
     decode(0, cur);
