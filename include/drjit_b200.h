@@ -159,7 +159,13 @@ DRJIT_B200_API int drjit_b200_compress(void *stream, const uint8_t *in, uint32_t
  * quadruples {bucket id, start, size, 0} of the non-empty buckets in ascending id order and
  * the unique count at offsets[4*bucket_count]; the count is also returned in *unique_out.
  * As in the reference (cuda_ts.cpp:953-967) the call waits only until the bucket table is
- * valid; `perm` is complete in stream order. bucket_count == 0: EFATAL. */
+ * valid; `perm` is complete in stream order. bucket_count == 0: EFATAL.
+ * Stability (include/drjit-core/jit.h:2404-2406): the permutation is stable -- equal keys keep their
+ * input order, bit-identical to the LLVM backend -- whenever the reference's "tiny" variant would
+ * apply (bucket_count * 4 bytes * 32 warps fit into shared memory: <= 1816 buckets on a B200), at
+ * every input size; dr.sort / dr.argsort (LSD radix passes with 256 buckets) depend on it. Inputs
+ * below 2^18 keys and block_size < size are stable up to 7264 buckets. Beyond that the keys of a
+ * bucket appear in unspecified order, like in the reference's "small" / "large" variants. */
 DRJIT_B200_API int drjit_b200_block_mkperm(void *stream, const uint32_t *values, uint32_t size,
                                            uint32_t block_size, uint32_t bucket_count,
                                            uint32_t *perm, uint32_t *offsets,
