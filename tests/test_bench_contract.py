@@ -1,0 +1,39 @@
+"""bench.py contract checks that need no GPU: the reference arm (the unmodified reference's CPU
+primitives from oracle/_ref) prints one JSON line with the agreed keys, rank > 0 stays silent."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra):
+    env = dict(os.environ, **env_extra)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_reference_arm_json_line():
+    lines = _run({"RANK": "0", "WORLD_SIZE": "1"})
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_reference_arm_other_ranks_are_silent():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2"}) == []
