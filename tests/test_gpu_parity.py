@@ -306,6 +306,31 @@ def test_prefix_sum_2_30_properties():
     assert np.array_equal(to_np(out, "u32"), exp)
 
 
+@pytest.mark.parametrize("vt", ["u8", "f16", "i32", "u32", "f32", "i64", "f64"])
+def test_block_prefix_reduce_short_blocks(vt):
+    """block sizes 2..8 on large arrays (scanned inside one thread by a dedicated kernel, with a
+    general-path tail): every op, all four variants, ragged sizes, in place"""
+    ops_for = ["add", "min", "max"] + ([] if vt[0] == "f" else ["mul", "and", "or"])
+    for size in [(1 << 17) + 13, (1 << 17) + 16 * 35]:
+        x = make_input(vt, size); xd = to_dev(x, vt)
+        for bs in range(2, 9):
+            for op in ops_for:
+                for ex, rev in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                    got = to_np(dr.block_prefix_reduce(OPS[op], xd, bs, ex, rev, vt=VT[vt]), vt)
+                    exp = capi.block_prefix_reduce(vt, op, x, bs, ex, rev, acc64=(vt[0] == "f"))
+                    if vt[0] == "f" and op == "add":
+                        assert_close(got, exp, vt, bs, f"{vt} prefix bs={bs} size={size}")
+                    else:
+                        assert np.array_equal(got, exp), (vt, op, bs, ex, rev, size)
+    y = xd.clone()
+    dr.block_prefix_reduce(OPS["add"], y, 4, True, False, vt=VT[vt], out=y)
+    exp = capi.block_prefix_reduce(vt, "add", x, 4, True, False, acc64=(vt[0] == "f"))
+    if vt[0] == "f":
+        assert_close(to_np(y, vt), exp, vt, 4, "in place")
+    else:
+        assert np.array_equal(to_np(y, vt), exp)
+
+
 @pytest.mark.parametrize("vt", ["u8", "u32", "u64", "i32", "i64"])
 def test_prefix_windowed_carry_many_tiles(vt):
     """Unsegmented scans on the TMA path with more tiles than CTAs (every CTA advances its carry
