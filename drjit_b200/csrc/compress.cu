@@ -26,7 +26,9 @@ static void launch_compress(cudaStream_t stream, CompressParams &p, Scratch &scr
     const DeviceProps &dev = device_props();
     auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * TILE;
-    static int occupancy = 0;
+    // (function attributes and occupancy are per device: one slot per device and instantiation)
+    static int occupancy_of[kMaxDevices] = {};
+    int &occupancy = occupancy_of[dev.device % kMaxDevices];
     if (occupancy == 0) {
         if (smem > 48 * 1024)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

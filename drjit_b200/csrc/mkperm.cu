@@ -776,7 +776,8 @@ static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_coun
 
 template <uint32_t THREADS, uint32_t KEY_BITS>
 static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t, uint32_t grid, uint32_t smem, uint32_t smem_max) {
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // (function attributes are per device)
+    bool &configured = configured_on[device_props().device % kMaxDevices];
     if (!configured) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max));
@@ -837,7 +838,8 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
         DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &unique_dev, pinned + 1, 0));
     }
 
-    static bool configured = false;
+    static bool configured_on[kMaxDevices] = {};       // (function attributes are per device)
+    bool &configured = configured_on[dev.device % kMaxDevices];
     if (!configured) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));

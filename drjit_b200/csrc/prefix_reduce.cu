@@ -32,7 +32,9 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     constexpr uint32_t smem = STAGES * Geom::TILE_BYTES;
     constexpr uint32_t threads = ScanRoles<SEG, STAGES>::THREADS;
 
-    static int occupancy = 0; // per instantiation
+    // (function attributes and occupancy are per device: one slot per device and instantiation)
+    static int occupancy_of[kMaxDevices] = {};
+    int &occupancy = occupancy_of[dev.device % kMaxDevices];
     if (occupancy == 0) {
         // (static + dynamic shared memory together may exceed the 48 KiB default)
         if (smem >= 32 * 1024)

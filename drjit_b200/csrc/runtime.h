@@ -37,6 +37,8 @@ struct Error : std::runtime_error {
         }                                                                                \
     } while (0)
 
+constexpr int kMaxDevices = 64;     // per-device caches of function attributes / occupancy
+
 struct DeviceProps {
     int device = -1;
     uint32_t sm_count = 0;
