@@ -898,7 +898,7 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     p.values = values; p.perm = perm; p.size = size; p.block_size = block_size;
     p.bucket_count = bucket_count; p.index_base = index_base;
     p.n_groups = ceil_div(size, block_size);
-    while ((1u << p.key_bits) < bucket_count) ++p.key_bits;
+    while (p.key_bits < 32 && (1ull << p.key_bits) < bucket_count) ++p.key_bits;
 
     if (use_tile_path(p.n_groups, size, bucket_count)) {
         // Where the reference's "tiny" variant applies (bucket_count * 4 B * 32 warps fit into shared
