@@ -113,11 +113,26 @@ Scratch::Scratch(cudaStream_t stream) : m_stream(stream) {
     }
     m_state->mutex.lock();
     if (!m_state->counters) {
-        DJB_CUDA_CHECK(cudaMalloc((void **) &m_state->counters, kZeroedCounters * sizeof(uint32_t)));
-        DJB_CUDA_CHECK(cudaMemset(m_state->counters, 0, kZeroedCounters * sizeof(uint32_t)));
-        DJB_CUDA_CHECK(cudaHostAlloc((void **) &m_state->pinned, kPinnedWords * sizeof(uint32_t),
-                                     cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(m_state->pinned, 0, kPinnedWords * sizeof(uint32_t));
+        // A constructor that throws never runs its destructor: release the stream's lock and
+        // leave the control block unallocated so that the next call starts over.
+        try {
+            uint32_t *counters = nullptr, *pinned = nullptr;
+            DJB_CUDA_CHECK(cudaMalloc((void **) &counters, kZeroedCounters * sizeof(uint32_t)));
+            cudaError_t rv = cudaMemset(counters, 0, kZeroedCounters * sizeof(uint32_t));
+            if (rv == cudaSuccess)
+                rv = cudaHostAlloc((void **) &pinned, kPinnedWords * sizeof(uint32_t),
+                                   cudaHostAllocMapped | cudaHostAllocPortable);
+            if (rv != cudaSuccess) {
+                cudaFree(counters);
+                DJB_CUDA_CHECK(rv);
+            }
+            memset(pinned, 0, kPinnedWords * sizeof(uint32_t));
+            m_state->counters = counters;
+            m_state->pinned = pinned;
+        } catch (...) {
+            m_state->mutex.unlock();
+            throw;
+        }
     }
 }
 

@@ -12,7 +12,8 @@
  *                same bin issue a single atomic (pays off for heavily contended bins);
  *   - PRIVATE  : bins small enough for shared memory (<= 55K 4-byte bins) are accumulated
  *                per CTA in shared memory and flushed once -- no L2 atomic traffic per element.
- * Float min/max use the signed/unsigned integer-atomic trick of cuda_scatter.cpp:74-106.
+ * Float min/max use the signed/unsigned integer-atomic trick of cuda_scatter.cpp:74-106; f16
+ * add/min/max use the two-wide f16 reductions with an identity partner (cuda_scatter.cpp:291-332).
  */
 #include "common.cuh"
 #include "runtime.h"
@@ -32,7 +33,6 @@ DJB_ATOMIC(OpAdd, uint32_t, atomicAdd(addr, v))
 DJB_ATOMIC(OpAdd, uint64_t, atomicAdd((unsigned long long *) addr, (unsigned long long) v))
 DJB_ATOMIC(OpAdd, float, atomicAdd(addr, v))
 DJB_ATOMIC(OpAdd, double, atomicAdd(addr, v))
-DJB_ATOMIC(OpAdd, __half, atomicAdd(addr, v))
 DJB_ATOMIC(OpMin, uint32_t, atomicMin(addr, v))
 DJB_ATOMIC(OpMin, int32_t, atomicMin(addr, v))
 DJB_ATOMIC(OpMin, uint64_t, atomicMin((unsigned long long *) addr, (unsigned long long) v))
@@ -56,6 +56,38 @@ DJB_ATOMIC(OpMin, double, if (!(v < 0.0)) atomicMin((long long *) addr, __double
 DJB_ATOMIC(OpMax, double, if (!(v < 0.0)) atomicMax((long long *) addr, __double_as_longlong(v));
                           else atomicMin((unsigned long long *) addr, (unsigned long long) __double_as_longlong(v)))
 #undef DJB_ATOMIC
+
+// f16 min/max: the hardware has only the two-wide form (sm_90+, `red.global.v2.f16.{min,max}`);
+// the other half of the aligned pair receives the identity (+inf / -inf), exactly as
+// cuda_scatter.cpp:307-332 does it. Like there, the partner of the last element of an
+// odd-sized target lies 2 bytes past its end (inside the same 4-byte word).
+template <bool IS_MIN>
+__device__ __forceinline__ void red_f16_minmax(__half *addr, __half v) {
+    const uint16_t ident = IS_MIN ? 0x7c00u : 0xfc00u, bits = __half_as_ushort(v);
+    const bool even = (((uintptr_t) addr) & 2u) == 0;
+    const uint16_t lo = even ? bits : ident, hi = even ? ident : bits;
+    const uintptr_t base = ((uintptr_t) addr) & ~(uintptr_t) 2;
+    if (IS_MIN)
+        asm volatile("red.global.v2.f16.min.noftz [%0], {%1, %2};" :: "l"(base), "h"(lo), "h"(hi) : "memory");
+    else
+        asm volatile("red.global.v2.f16.max.noftz [%0], {%1, %2};" :: "l"(base), "h"(lo), "h"(hi) : "memory");
+}
+// f16 add: atomicAdd(__half *) compiles to a compare-and-swap loop; the packed form with a zero
+// partner is a native fire-and-forget reduction (cuda_scatter.cpp:291-306 makes the same choice)
+template <> struct AtomicOp<OpAdd, __half> {
+    static __device__ __forceinline__ void apply(__half *addr, __half v) {
+        const uint32_t bits = __half_as_ushort(v);
+        const uint32_t packed = (((uintptr_t) addr) & 2u) ? bits << 16 : bits;
+        asm volatile("red.global.add.noftz.f16x2 [%0], %1;"
+                     :: "l"(((uintptr_t) addr) & ~(uintptr_t) 2), "r"(packed) : "memory");
+    }
+};
+template <> struct AtomicOp<OpMin, __half> {
+    static __device__ __forceinline__ void apply(__half *addr, __half v) { red_f16_minmax<true>(addr, v); }
+};
+template <> struct AtomicOp<OpMax, __half> {
+    static __device__ __forceinline__ void apply(__half *addr, __half v) { red_f16_minmax<false>(addr, v); }
+};
 
 struct ScatterParams {
     void *target;
@@ -277,7 +309,11 @@ void scatter_reduce(cudaStream_t stream, int vt, int op, int mode, void *target,
             else unsupported();
             break;
         case DRJIT_B200_VT_FLOAT16:
-            if (op == DRJIT_B200_OP_ADD) DJB_SC(__half, OpAdd); else unsupported();
+            // min/max need cc >= 90 in the reference (op.cpp:2786-2794); always true here
+            if (op == DRJIT_B200_OP_ADD) DJB_SC(__half, OpAdd);
+            else if (op == DRJIT_B200_OP_MIN) DJB_SC(__half, OpMin);
+            else if (op == DRJIT_B200_OP_MAX) DJB_SC(__half, OpMax);
+            else unsupported();
             break;
         case DRJIT_B200_VT_FLOAT32:
             if (op == DRJIT_B200_OP_ADD) DJB_SC(float, OpAdd);

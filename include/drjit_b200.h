@@ -186,7 +186,10 @@ DRJIT_B200_API int drjit_b200_aggregate(void *stream, void *dst,
  * mode: Auto/Local = warp-level pre-reduction of equal indices + privatised shared-memory
  * bins when the target fits; Direct = one atomic per element. Supported (op, type) pairs
  * follow the reference's capability table (src/op.cpp:2735-2822): Add: i32,u32,i64,u64,f16,f32,f64;
- * Min/Max: i32,u32,i64,u64,f32,f64; And/Or: i32,u32,i64,u64. Others: EUNSUPPORTED. */
+ * Min/Max: i32,u32,i64,u64,f16,f32,f64; And/Or: i32,u32,i64,u64. Others: EUNSUPPORTED.
+ * f16 uses the two-wide f16 reductions with an identity partner (src/cuda_scatter.cpp:291-332):
+ * like the reference, the 4-byte word holding the last element of an odd-sized target is
+ * touched in full. */
 DRJIT_B200_API int drjit_b200_scatter_reduce(void *stream, int vt, int op, int mode, void *target,
                                              uint32_t target_size, const void *value,
                                              const uint32_t *index, const uint8_t *mask,

@@ -631,6 +631,34 @@ def test_scatter_reduce_other_ops(op):
             assert np.array_equal(got, exp), (vt, op, mode)
 
 
+@pytest.mark.parametrize("op", ["add", "min", "max"])
+@pytest.mark.parametrize("misalign", [0, 1])
+def test_scatter_reduce_f16(op, misalign):
+    """f16 scatter-reductions: add since cc 60, min/max since cc 90 (src/op.cpp:2781-2794); the CUDA
+    form is the two-wide f16 reduction with an identity partner (src/cuda_scatter.cpp:291-332).
+    Sums of small integers are exact in f16, so every comparison here is bit-for-bit (-0 == +0)."""
+    n, bins = 40_003, 501           # odd bin count: the last element has no partner inside the array
+    idx = capi.fmix32(n, xor=3) % np.uint32(bins)
+    mask = (capi.fmix32(n, xor=4) & 7) != 0
+    if op == "add":
+        val = (capi.fmix32(n, xor=5) % np.uint32(8)).astype(np.float16)     # bin sums < 2048: exact
+        init = (capi.fmix32(bins, xor=6) % np.uint32(16)).astype(np.float16)
+    else:
+        val = make_input("f16", n)
+        init = make_input("f16", bins)
+    exp = capi.scatter_reduce("f16", op, init, val, idx, mask=mask.astype(np.uint8))
+    for mode in (ReduceMode.Auto, ReduceMode.Direct, ReduceMode.Local):
+        tgt = to_dev(init, "f16", misalign=misalign)
+        got = to_np(dr.scatter_reduce(OPS[op], tgt, to_dev(val, "f16"), to_dev(idx, "u32"),
+                                      active=torch.from_numpy(mask).cuda(), mode=mode), "f16")
+        assert np.array_equal(got, exp), (op, mode, misalign)
+    for bad in ("and", "or", "mul"):
+        with pytest.raises(RuntimeError, match="does not support"):
+            dr.scatter_reduce(OPS[bad], torch.zeros(4, dtype=torch.float16, device="cuda"),
+                              torch.zeros(4, dtype=torch.float16, device="cuda"),
+                              torch.zeros(4, dtype=torch.int32, device="cuda"))
+
+
 def test_scatter_add_baseline_config():
     """BASELINE config 5 (one shard): 2^25 f32 values into 2^20 bins; tolerance 1e-6*log2(count)"""
     n, bins = 1 << 25, 1 << 20
