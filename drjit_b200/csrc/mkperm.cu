@@ -367,6 +367,7 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
 //  as the reference's "small"/"large" variants, jit.h:2404-2406); bucket boundaries, the offsets
 //  table and per-bucket contents are exact.
 constexpr uint32_t kTileKeysPerThread = 32;
+constexpr uint32_t kMkpermDefaultKpt = 48;  // largest tile of the unordered kernel, keys per thread (see mkperm_impl)
 constexpr uint32_t kTileMaxBuckets = 8192;
 
 struct MkpermTileParams {
@@ -404,10 +405,37 @@ __device__ __forceinline__ void tile_load_keys(const MkpermTileParams &p, uint64
     }
 }
 
-template <uint32_t THREADS>
+/// Same for tiles of more than 32 keys per thread: two keys per register (bucket ids on the tile
+/// path are < 8192; 0xffff marks a slot past the end), key k = half (k & 1) of kp[k >> 1], same
+/// local indices as above.
+template <uint32_t THREADS, uint32_t KPT>
+__device__ __forceinline__ void tile_load_keys_packed(const MkpermTileParams &p, uint64_t tile_base, uint32_t n_tile,
+                                                      uint32_t (&kp)[KPT / 2]) {
+    static_assert(KPT % 4 == 0, "keys are loaded four at a time");
+    const uint32_t tid = threadIdx.x, last = p.bucket_count - 1;
+    if (p.vec && n_tile == THREADS * KPT) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(p.values + tile_base);
+        #pragma unroll
+        for (uint32_t k = 0; k < KPT / 4; ++k) {
+            const Vec16<uint32_t> t = ld_stream<uint32_t>(v + k * THREADS + tid);
+            kp[2 * k] = min(t.v[0], last) | (min(t.v[1], last) << 16);
+            kp[2 * k + 1] = min(t.v[2], last) | (min(t.v[3], last) << 16);
+        }
+    } else {
+        #pragma unroll
+        for (uint32_t k = 0; k < KPT / 2; ++k) {
+            const uint32_t i0 = (2 * k) * THREADS + tid, i1 = i0 + THREADS;
+            const uint32_t a = i0 < n_tile ? min(__ldg(p.values + tile_base + i0), last) : 0xffffu,
+                           b = i1 < n_tile ? min(__ldg(p.values + tile_base + i1), last) : 0xffffu;
+            kp[k] = a | (b << 16);
+        }
+    }
+}
+
+template <uint32_t THREADS, uint32_t KPT = kTileKeysPerThread>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_hist_kernel(const MkpermTileParams p) {
-    constexpr uint32_t TILE = THREADS * kTileKeysPerThread;
+    constexpr uint32_t TILE = THREADS * KPT;
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t S = p.stride;
     uint32_t *hist = smem;                                  // running counts of this chunk
@@ -434,16 +462,26 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
     for (uint32_t tile = first; tile < end; ++tile) {
         const uint64_t tile_base = (uint64_t) tile * TILE;
         const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
-        uint32_t key[kTileKeysPerThread];
-        tile_load_keys<THREADS>(p, tile_base, n_tile, key);      // loads in flight across the barrier
+        constexpr bool PACKED = KPT > kTileKeysPerThread;
+        uint32_t key[PACKED ? KPT / 2 : KPT];
+        if constexpr (PACKED)
+            tile_load_keys_packed<THREADS, KPT>(p, tile_base, n_tile, key);
+        else
+            tile_load_keys<THREADS>(p, tile_base, n_tile, key);  // loads in flight across the barrier
         if (tid == 0 && p.vec && tile + 1 < end && (uint64_t) (tile + 2) * TILE <= p.size)
             bulk_prefetch_l2(p.values + (uint64_t) (tile + 1) * TILE, TILE * 4);
         __syncthreads();                                    // previous tile's atomics are done
         snapshot(tile);
         __syncthreads();
         #pragma unroll
-        for (uint32_t k = 0; k < kTileKeysPerThread; ++k)
-            if (key[k] != 0xffffffffu) atomicAdd(hist + key[k], 1u);
+        for (uint32_t k = 0; k < KPT; ++k) {
+            if constexpr (PACKED) {
+                const uint32_t b = (key[k >> 1] >> (16 * (k & 1u))) & 0xffffu;
+                if (b != 0xffffu) atomicAdd(hist + b, 1u);
+            } else {
+                if (key[k] != 0xffffffffu) atomicAdd(hist + key[k], 1u);
+            }
+        }
     }
     __syncthreads();
     snapshot(end);
@@ -451,10 +489,11 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
     for (uint32_t b = tid; b < S; b += THREADS) row[b] = hist[b];
 }
 
-template <uint32_t THREADS>
+template <uint32_t THREADS, uint32_t KPT = kTileKeysPerThread>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_scatter_kernel(const MkpermTileParams p) {
-    constexpr uint32_t TILE = THREADS * kTileKeysPerThread, WARPS = THREADS / 32;
+    constexpr uint32_t TILE = THREADS * KPT, WARPS = THREADS / 32;
+    constexpr bool PACKED = KPT > kTileKeysPerThread;
     static_assert(TILE <= 65536, "local indices are packed into 16 bits");
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t S = p.stride;
@@ -469,8 +508,11 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
         const bool vec = p.vec && n_tile == TILE;
 
-        uint32_t key[kTileKeysPerThread];
-        tile_load_keys<THREADS>(p, tile_base, n_tile, key);     // in flight during the bin phase
+        uint32_t key[PACKED ? KPT / 2 : KPT];
+        if constexpr (PACKED)
+            tile_load_keys_packed<THREADS, KPT>(p, tile_base, n_tile, key);
+        else
+            tile_load_keys<THREADS>(p, tile_base, n_tile, key); // in flight during the bin phase
         // Ask L2 for everything the next tile of this CTA will read, so that its loads see an L2
         // round trip instead of DRAM latency (the kernel was latency-bound: profiles/r1d)
         if (tid == 0) {
@@ -542,10 +584,15 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         // ---- (2) keys: slot from the bucket's cursor, entry stored at the slot ---------------
         #pragma unroll
-        for (uint32_t k = 0; k < kTileKeysPerThread; ++k) {
-            if (key[k] != 0xffffffffu) {
-                const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
-                sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
+        for (uint32_t k = 0; k < KPT; ++k) {
+            const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
+            if constexpr (PACKED) {
+                const uint32_t b = (key[k >> 1] >> (16 * (k & 1u))) & 0xffffu;
+                if (b != 0xffffu)
+                    sorted[atomicAdd(cursor + b, 1u)] = (b << 16) | local;
+            } else {
+                if (key[k] != 0xffffffffu)
+                    sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
             }
         }
         __syncthreads();
@@ -786,11 +833,12 @@ static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t
     mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS><<<grid, THREADS, smem, stream>>>(t);
 }
 
-template <uint32_t THREADS, bool STABLE>
+template <uint32_t THREADS, bool STABLE, uint32_t KPT = kTileKeysPerThread>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
                              uint32_t *offsets, uint32_t *hist_out) {
-    constexpr uint32_t TILE = THREADS * kTileKeysPerThread;
+    static_assert(!STABLE || KPT == kTileKeysPerThread, "the stable kernel has 32 keys per thread");
+    constexpr uint32_t TILE = THREADS * KPT;
     const DeviceProps &dev = device_props();
     MkpermTileParams t{};
     t.values = values; t.perm = perm; t.size = size; t.bucket_count = bucket_count;
@@ -841,15 +889,17 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     static bool configured_on[kMaxDevices] = {};       // (function attributes are per device)
     bool &configured = configured_on[dev.device % kMaxDevices];
     if (!configured) {
-        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));
         if (!STABLE)
-            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int) (kTileMaxBuckets * 8 + TILE * 4)));
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4, dev.smem_optin - 1024)));
         configured = true;
     }
+    if (!STABLE && scatter_smem > dev.smem_optin - 1024)
+        raise(DRJIT_B200_EFATAL, "jit_block_mkperm(): internal error (tile does not fit into shared memory)");
 
-    mkperm_tile_hist_kernel<THREADS><<<chunks, THREADS, hist_smem, stream>>>(t);
+    mkperm_tile_hist_kernel<THREADS, KPT><<<chunks, THREADS, hist_smem, stream>>>(t);
     DJB_POST_LAUNCH();
     const uint32_t col_tiles = ceil_div(bucket_count, 32);
     mkperm_column_scan_kernel<<<col_tiles, 256, 0, stream>>>(p, col_tiles);
@@ -869,7 +919,7 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     } else {
         const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
         const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
-        mkperm_tile_scatter_kernel<THREADS><<<grid, THREADS, scatter_smem, stream>>>(t);
+        mkperm_tile_scatter_kernel<THREADS, KPT><<<grid, THREADS, scatter_smem, stream>>>(t);
     }
     DJB_POST_LAUNCH();
 
@@ -918,6 +968,24 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
             return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         if (stable)                             // 16 rows + a 16 Ki-key tile (up to 1816 buckets)
             return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        // Unordered kernel: what bounds its scatter pass is the length of a bucket's run per tile
+        // (profiles/r1b_microbench.txt), so the tile is as large as shared memory allows: 48 Ki keys
+        // (two 16-bit keys per register) next to the two bucket rows up to 4352 buckets, 32 Ki keys
+        // then 40 Ki keys up to 8192. DRJIT_B200_MKPERM_KPT=32|40|48 caps the tile (A/B measurements only).
+        static int kpt_env = -1;
+        if (kpt_env < 0) {
+            const char *env = getenv("DRJIT_B200_MKPERM_KPT");
+            kpt_env = env ? atoi(env) : 0;
+        }
+        const uint32_t stride = (bucket_count + 7) / 8 * 8;
+        auto fits = [&](uint32_t kpt) {
+            return stride * 8 + 1024 * kpt * 4 <= dev.smem_optin - 1024 && size >= dev.sm_count * 2u * 1024u * kpt;
+        };
+        const uint32_t kpt = kpt_env ? (uint32_t) kpt_env : kMkpermDefaultKpt;
+        if (kpt >= 48 && fits(48))
+            return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        if (kpt >= 40 && fits(40))
+            return mkperm_tiles<1024, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
     }
 

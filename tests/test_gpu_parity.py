@@ -581,6 +581,26 @@ def test_mkperm_baseline_config():
     check_mkperm(keys, 4096, to_np(perm, "u32"), table)
 
 
+@pytest.mark.parametrize("buckets", [1817, 4096, 4352, 4353, 8192])
+def test_mkperm_unordered_tiles_ragged_unaligned(buckets):
+    """unordered tile kernel (beyond the reference's stable range) at sizes where the largest tile
+    applies: ragged last tile, input not 16-byte aligned, keys drawn from all / from few buckets"""
+    n = 148 * 2 * 48 * 1024 + 12_345
+    buf = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    for mis in (0, 1):
+        kd = buf[mis:mis + n]
+        dr.ops.fill_fmix32(kd, 0, xor=buckets)
+        kd.remainder_(buckets)
+        perm, table = dr.block_mkperm(kd, n, buckets)
+        torch.cuda.synchronize()
+        check_mkperm_device(kd, buckets, perm, table)
+    kd = buf[:n]
+    kd.remainder_(3).mul_(buckets // 3)                   # three buckets hold everything
+    perm, table = dr.block_mkperm(kd, n, buckets)
+    torch.cuda.synchronize()
+    check_mkperm_device(kd, buckets, perm, table)
+
+
 def test_mkperm_errors():
     k = torch.zeros(10, dtype=torch.int32, device="cuda")
     with pytest.raises(dr._lib.FatalError, match="bucket_count cannot be zero"):
