@@ -379,6 +379,8 @@ struct MkpermTileParams {
     const uint32_t *bucket_start; // [buckets] after the bucket scan
     uint32_t size, bucket_count, stride, tiles, tiles_per_chunk, index_base;
     uint8_t vec;
+    uint8_t debug;           // timing experiments only (DRJIT_B200_MKPERM_DEBUG; results are wrong when set):
+                             // 1 = copy-out without its global stores, 2 = no copy-out, 4 = no ranking, 8 = no bucket rows
 };
 
 /// Loads the keys of one tile into registers (clamped to the last bucket: out-of-range keys are
@@ -526,7 +528,7 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         }
 
         // ---- (1) bins: thread t owns 8 consecutive buckets per round ----------------------
-        {
+        if (!(p.debug & 8u)) {
             const uint32_t chunk = tile / p.tiles_per_chunk;
             const uint16_t *cnt = p.tile_cnt + (size_t) tile * S;
             const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
@@ -583,26 +585,42 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         }
 
         // ---- (2) keys: slot from the bucket's cursor, entry stored at the slot ---------------
-        #pragma unroll
-        for (uint32_t k = 0; k < KPT; ++k) {
-            const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
-            if constexpr (PACKED) {
-                const uint32_t b = (key[k >> 1] >> (16 * (k & 1u))) & 0xffffu;
-                if (b != 0xffffu)
-                    sorted[atomicAdd(cursor + b, 1u)] = (b << 16) | local;
-            } else {
-                if (key[k] != 0xffffffffu)
-                    sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
+        if (!(p.debug & 4u)) {
+            #pragma unroll
+            for (uint32_t k = 0; k < KPT; ++k) {
+                const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
+                if constexpr (PACKED) {
+                    const uint32_t b = (key[k >> 1] >> (16 * (k & 1u))) & 0xffffu;
+                    if (b != 0xffffu)
+                        sorted[atomicAdd(cursor + b, 1u)] = (b << 16) | local;
+                } else {
+                    if (key[k] != 0xffffffffu)
+                        sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
+                }
             }
+        } else {
+            uint32_t x = 0;                             // (keeps the key loads alive)
+            #pragma unroll
+            for (uint32_t k = 0; k < (PACKED ? KPT / 2 : KPT); ++k) x ^= key[k];
+            if (x == 0x12345678u) sorted[tid] = x;
         }
         __syncthreads();
 
         // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        #pragma unroll 4
-        for (uint32_t j = tid; j < n_tile; j += THREADS) {
-            const uint32_t e = sorted[j];
-            p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+        if (!p.debug) {
+            #pragma unroll 4
+            for (uint32_t j = tid; j < n_tile; j += THREADS) {
+                const uint32_t e = sorted[j];
+                p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+            }
+        } else if (p.debug == 1u) {
+            #pragma unroll 4
+            for (uint32_t j = tid; j < n_tile; j += THREADS) {
+                const uint32_t e = sorted[j];
+                const uint32_t at = delta[e >> 16] + j;
+                if (at == 0xfffffff1u) p.perm[0] = idx0 + (e & 0xffffu);
+            }
         }
         __syncthreads();
     }
@@ -846,6 +864,14 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     t.index_base = index_base;
     t.tiles = (uint32_t) ceil_div64(size, TILE);
     t.vec = ((uintptr_t) values % 16) == 0;
+    {
+        static int debug = -1;
+        if (debug < 0) {
+            const char *env = getenv("DRJIT_B200_MKPERM_DEBUG");
+            debug = env ? atoi(env) : 0;
+        }
+        t.debug = (uint8_t) debug;
+    }
 
     const uint32_t hist_smem = t.stride * 8,
                    scatter_smem = STABLE ? (THREADS / 32 + 1) * t.stride * 4 + TILE * 4
