@@ -1008,11 +1008,8 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
             return stride * 8 + 1024 * kpt * 4 <= dev.smem_optin - 1024 && size >= dev.sm_count * 2u * 1024u * kpt;
         };
         const uint32_t kpt = kpt_env ? (uint32_t) kpt_env : kMkpermDefaultKpt;
-        // (experiments: two 512-thread CTAs per SM with 20 Ki / 16 Ki-key tiles)
-        if (kpt_env == 540 && stride * 8 + 512 * 40 * 4 <= (dev.smem_optin - 2048) / 2)
-            return mkperm_tiles<512, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
-        if (kpt_env == 532)
-            return mkperm_tiles<512, false, 32>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+        // (two co-resident 512-thread CTAs with 20 Ki / 16 Ki-key tiles were measured and are slower:
+        // 0.396 / 0.499 ms against 0.348 ms, profiles/r2o_mkperm_tile_keys.txt)
         if (kpt >= 48 && fits(48))
             return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         if (kpt >= 40 && fits(40))
