@@ -1,0 +1,75 @@
+"""CPU-only static check of the shipped sm_100a code: the hot kernels contain the instruction
+classes DESIGN.md section 4 claims (TMA bulk copies + mbarriers in scan / compress, redux.sync,
+128-bit accesses, shared atomics + L2 bulk prefetch in mkperm, native global reductions incl. the
+two-wide f16 forms in scatter_reduce). Full listing: scripts/sass_evidence.py -> profiles/sass_evidence.txt."""
+import functools
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "drjit_b200", "lib", "libdrjit_b200.so")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+SCAN = "_ZN3djb20prefix_reduce_kernelIjNS_5OpAddELb0ELb1ELj8ELj3ELj2EEEvNS_12PrefixParamsE"
+COMPRESS = "_ZN3djb15compress_kernelILj8ELj1ELj3EEEvNS_14CompressParamsE"
+SUM = "_ZN3djb25block_reduce_chunk_kernelIfNS_5OpAddELb0ELb1EEEvPKT_S4_PS2_PNS_3AccIS2_E4typeEPjjjjj"
+MKPERM_SCATTER = "_ZN3djb26mkperm_tile_scatter_kernelILj1024ELj%uEEEvNS_16MkpermTileParamsE"
+MKPERM_HIST = "_ZN3djb23mkperm_tile_hist_kernelILj1024ELj48EEEvNS_16MkpermTileParamsE"
+MKPERM_STABLE = "_ZN3djb33mkperm_tile_scatter_stable_kernelILj1024ELj8EEEvNS_16MkpermTileParamsE"
+SCATTER = "_ZN3djb21scatter_reduce_kernelI%sNS_5Op%sELb0EEEvNS_13ScatterParamsE"
+
+
+@functools.lru_cache(maxsize=None)
+def sass(mangled):
+    """SASS of one kernel of the shipped library (cuobjdump warns on stderr for every other cubin)"""
+    assert os.path.exists(LIB), "run __graft_entry__.build() first"
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, LIB], capture_output=True, text=True).stdout
+    assert "Function : " + mangled in out, f"kernel {mangled} is not in the library"
+    assert "arch = sm_100a" in out
+    return out
+
+
+def test_only_sm_100a_code_is_shipped():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], check=True, capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("kernel", [SCAN, COMPRESS])
+def test_scan_and_compress_are_tma_staged(kernel):
+    b = sass(kernel)
+    assert re.search(r"\bUBLKCP", b), "no cp.async.bulk"
+    assert re.search(r"\bSYNCS", b), "no mbarrier"
+    assert re.search(r"\bC?REDUX", b), "no redux.sync"
+    assert re.search(r"\bLDS\.128", b), "no 128-bit shared loads"
+
+
+def test_reductions_use_wide_loads_and_shuffles():
+    b = sass(SUM)
+    assert re.search(r"\bLDG\.E\.\S*128", b)
+    assert re.search(r"\bSHFL", b)
+
+
+@pytest.mark.parametrize("kernel", [MKPERM_SCATTER % 48, MKPERM_SCATTER % 40, MKPERM_SCATTER % 32, MKPERM_HIST])
+def test_mkperm_tile_kernels(kernel):
+    b = sass(kernel)
+    assert re.search(r"\bATOMS", b), "no shared atomics"
+    assert re.search(r"\bUBLKPF", b), "no L2 bulk prefetch"
+    assert re.search(r"\bLDG\.E\.\S*128", b), "keys are not read with 128-bit loads"
+
+
+def test_stable_mkperm_ranks_with_ballots():
+    assert len(re.findall(r"\bVOTEU?\b", sass(MKPERM_STABLE))) >= 256
+
+
+def test_scatter_reduce_uses_native_reductions():
+    assert re.search(r"\bREDG?\.E\.ADD\.F32", sass(SCATTER % ("f", "Add")))
+    for op in ("Add", "Min", "Max"):
+        b = sass(SCATTER % ("6__half", op))
+        assert re.search(rf"\bREDG?\.E\.{op.upper()}\.F16x2", b), f"f16 {op}: not a two-wide f16 reduction"
+        assert not re.search(r"\bATOMG?\.E\.CAS", b), f"f16 {op}: compare-and-swap loop"
