@@ -53,6 +53,31 @@ class Sharded:
         allp = self._all_gather(part)
         return self.local.block_reduce(op, allp, allp.numel(), vt=vt)
 
+    def block_reduce(self, op, x, block_size, vt=None, out=None):
+        """dr.block_reduce over the global array. Shards cut at multiples of ``block_size``
+        (``shard_range(n, align=block_size)``) hold whole blocks, so every rank reduces its own
+        blocks and the global result is the rank-order concatenation: no collective."""
+        return self.local.block_reduce(op, x, block_size, vt=vt, out=out)
+
+    def _all_any(self, mask, want_all):
+        if mask.numel() == 0:
+            flag = want_all                     # identity of And / Or (empty trailing shard)
+        else:
+            flag = self.local.all(mask) if want_all else self.local.any(mask)
+        if self.world == 1:
+            return bool(flag)
+        t = torch.tensor([int(bool(flag))], dtype=torch.int32, device=mask.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN if want_all else dist.ReduceOp.MAX, group=self.group)
+        return bool(int(t.item()))
+
+    def all(self, mask):    # noqa: A003
+        """dr.all over the global mask (synchronous like jitc_all): local flag, one 4-byte all-reduce (min)."""
+        return self._all_any(mask, True)
+
+    def any(self, mask):    # noqa: A003
+        """dr.any over the global mask: local flag, one 4-byte all-reduce (max)."""
+        return self._all_any(mask, False)
+
     def dot(self, a, b):
         part = self.local.dot(a, b)
         if self.world == 1:

@@ -38,6 +38,12 @@ class OracleLocal:
         t, a = self._np(x)
         return self._t(capi.block_reduce(t, _OPN[int(op)], a, block_size, acc64=True), x)
 
+    def all(self, mask):    # noqa: A003
+        return bool(np.all(mask.numpy() != 0))
+
+    def any(self, mask):    # noqa: A003
+        return bool(np.any(mask.numpy() != 0))
+
     def dot(self, a, b):
         return torch.tensor([float(capi.reduce_dot("f32", a.numpy(), b.numpy(), acc64=True))], dtype=torch.float32)
 
@@ -92,6 +98,23 @@ def _worker(rank, world, port, n):
         for op, name in ((ReduceOp.Add, "add"), (ReduceOp.Min, "min"), (ReduceOp.Max, "max")):
             got = sh.reduce(op, ut).numpy().view(np.uint32)[0]
             assert got == capi.block_reduce("u32", name, u, n)[0], name
+
+        # block_reduce: shards cut at block boundaries reduce independently, outputs concatenate
+        got = sh.block_reduce(ReduceOp.Add, ut, 256).numpy().view(np.uint32)
+        exp = capi.block_reduce("u32", "add", u, 256)
+        assert np.array_equal(got, exp[lo // 256: lo // 256 + got.size]) and got.size == -(-(hi - lo) // 256)
+        pieces = [None] * world
+        dist.all_gather_object(pieces, got.size)
+        assert sum(pieces) == exp.size
+
+        # all / any: every rank sees the global answer, whichever shard holds the deciding byte
+        for pos in (0, n - 1, n // 2):
+            ones = np.ones(n, np.uint8); ones[pos] = 0
+            zeros = np.zeros(n, np.uint8); zeros[pos] = 1
+            assert sh.all(torch.from_numpy(ones[lo:hi].copy())) is False
+            assert sh.any(torch.from_numpy(zeros[lo:hi].copy())) is True
+        assert sh.all(torch.ones(hi - lo, dtype=torch.uint8)) is True
+        assert sh.any(torch.zeros(hi - lo, dtype=torch.uint8)) is False
 
         # distributed exclusive prefix sum == slice of the single-array oracle scan (bit-exact)
         got = sh.prefix_sum(ut).numpy().view(np.uint32)

@@ -39,6 +39,16 @@ def _worker(rank, world, port, n):
             got = sh.reduce(op, ut, vt=VarType.UInt32).cpu().numpy().view(np.uint32)[0]
             assert got == capi.block_reduce("u32", name, u, n)[0], name
 
+        got = sh.block_reduce(ReduceOp.Add, ut, 256, vt=VarType.UInt32).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, capi.block_reduce("u32", "add", u, 256)[lo // 256: lo // 256 + got.size])
+
+        ones = np.ones(n, np.uint8); ones[n - 1] = 0
+        zeros = np.zeros(n, np.uint8); zeros[0] = 1
+        assert sh.all(torch.from_numpy(ones[lo:hi].copy()).to(dev)) is False
+        assert sh.any(torch.from_numpy(zeros[lo:hi].copy()).to(dev)) is True
+        assert sh.all(torch.ones(hi - lo, dtype=torch.uint8, device=dev)) is True
+        assert sh.any(torch.zeros(hi - lo, dtype=torch.uint8, device=dev)) is False
+
         got = sh.prefix_sum(ut, vt=VarType.UInt32).cpu().numpy().view(np.uint32)
         assert np.array_equal(got, capi.block_prefix_reduce("u32", "add", u, n, True, False)[lo:hi])
 
