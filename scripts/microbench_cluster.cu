@@ -105,6 +105,64 @@ static void run(int sms, uint32_t *out, size_t out_words, uint32_t n_log2) {
            T / 1024, B, C, cfg.gridDim.x, R * C, best, bytes / best / 1e6);
 }
 
+// Rate of scattered 4-byte shared-memory stores when a fraction of them goes to the other CTAs of
+// the cluster (option (ii) of DESIGN.md section 8.1: entries ranked locally, stored straight into the
+// owner CTA's staging buffer). MODE 0: plain stores, 1: returning atomicAdd on the (remote) word.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16; return h;
+}
+
+template <uint32_t C, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) remote_scatter(uint32_t *sink, uint32_t words_mask, uint32_t iters) {
+    extern __shared__ __align__(16) uint32_t buf[];
+    cg::cluster_group cluster = cg::this_cluster();
+    for (uint32_t j = threadIdx.x; j <= words_mask; j += kThreads) buf[j] = 0;
+    uint32_t *peer[C];
+    #pragma unroll
+    for (uint32_t q = 0; q < C; ++q) peer[q] = C > 1 ? cluster.map_shared_rank(buf, q) : buf;
+    if (C > 1) cluster.sync(); else __syncthreads();
+    uint32_t acc = 0;
+    const uint32_t seed = (blockIdx.x * kThreads + threadIdx.x) * iters;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t h = fmix32(seed + it);
+        uint32_t *dst = peer[0];
+        #pragma unroll
+        for (uint32_t q = 1; q < C; ++q) if ((h >> 28) % C == q) dst = peer[q];     // uniform choice of the owner
+        if (MODE == 0) dst[h & words_mask] = it;
+        else acc += atomicAdd(dst + (h & words_mask), 1u);
+    }
+    if (C > 1) cluster.sync(); else __syncthreads();
+    if (acc == 0x12345678u) sink[0] = acc + buf[threadIdx.x];
+}
+
+template <uint32_t C, int MODE>
+static void run_remote(int sms, uint32_t *sink, int clk_khz) {
+    const uint32_t words = 32768, smem = words * 4, iters = 4096;
+    CK(cudaFuncSetAttribute(remote_scatter<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((uint32_t) (sms / C * C)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int clusters = 0;
+    CK(cudaOccupancyMaxActiveClusters(&clusters, remote_scatter<C, MODE>, &cfg));
+    if (C > 1 && (uint32_t) clusters * C < cfg.gridDim.x) cfg.gridDim = dim3(clusters * C);
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int i = 0; i < 4; ++i) {
+        CK(cudaEventRecord(a));
+        CK(cudaLaunchKernelEx(&cfg, remote_scatter<C, MODE>, sink, words - 1, iters));
+        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        if (i && ms < best) best = ms;
+    }
+    const double ops = (double) cfg.gridDim.x * kThreads * iters;
+    printf("scattered 4-byte %s into 128 KB, cluster %u (%u%% remote, grid %3u): %8.3f ms  %6.2f per clk and SM\n",
+           MODE ? "shared atomicAdd (ret)" : "shared stores         ", C, C > 1 ? 100 * (C - 1) / C : 0, cfg.gridDim.x, best,
+           ops / (best * 1e-3) / cfg.gridDim.x / (clk_khz * 1e3));
+}
+
 int main() {
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     const size_t out_words = (size_t) 80 << 20;                         // 2^26 entries + padding
@@ -118,5 +176,10 @@ int main() {
     run<48, 4096, 4>(sms, out, out_words, n_log2);
     run<32, 256, 1>(sms, out, out_words, n_log2);                       // long runs: the streaming limit of this loop
     CK(cudaFree(out));
+
+    int clk = 0; CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0));
+    uint32_t *sink; CK(cudaMalloc(&sink, 64));
+    run_remote<1, 0>(sms, sink, clk); run_remote<2, 0>(sms, sink, clk); run_remote<4, 0>(sms, sink, clk);
+    run_remote<1, 1>(sms, sink, clk); run_remote<2, 1>(sms, sink, clk);
     return 0;
 }
