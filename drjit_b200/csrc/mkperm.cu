@@ -627,6 +627,193 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 }
 
 // ---------------------------------------------------------------------------
+//  Unordered tile scatter with 16-bit staging entries (EXPERIMENTAL: DRJIT_B200_MKPERM_KPT=60)
+// ---------------------------------------------------------------------------
+//  DESIGN.md section 8.1, step (1). The staged entry is the key's 16-bit local index only, which
+//  lets a tile hold 60 Ki keys (runs per bucket and tile are what the store path of the copy-out is
+//  bound by). The copy-out recovers a slot's bucket with a rank query instead of reading it from
+//  the entry: one bit per non-empty bucket start in a bitmap over the tile's slots, a 16-bit prefix
+//  count per bitmap word, and a table rank -> bucket. A warp copies 32 aligned slots, so the bitmap
+//  word and the prefix count are warp-uniform loads and the rank is one popcount.
+//  Keys are not held in registers: they are ranked in groups of 20 per thread (5 x LDG.128).
+//  Written after the GPU budget of round 1 was spent: compiles, selected only by the environment
+//  variable above, not yet run on hardware (tests/test_gpu_parity.py -k mkperm with that variable
+//  set is the acceptance test).
+template <uint32_t THREADS, uint32_t KPT>
+__global__ void __launch_bounds__(THREADS, 1)
+mkperm_tile_scatter16_kernel(const MkpermTileParams p) {
+    constexpr uint32_t TILE = THREADS * KPT, WARPS = THREADS / 32, WORDS = TILE / 32, GROUP = 5;
+    static_assert(TILE < 65536, "tile counts and local indices are 16-bit values");
+    static_assert(KPT % (4 * GROUP) == 0, "keys are ranked in groups of 20 per thread");
+    static_assert(WORDS <= 2 * THREADS, "two bitmap words per thread in the prefix count");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t S = p.stride;
+    uint32_t *cursor = smem;                                    // [S] next free slot of the bucket
+    uint32_t *delta = smem + S;                                 // [S] final position of the run minus its local start
+    uint32_t *bitmap = smem + 2 * S;                            // [WORDS] bit s: a non-empty bucket starts at slot s
+    uint16_t *wrank = reinterpret_cast<uint16_t *>(bitmap + WORDS);       // [WORDS] set bits before the word
+    uint16_t *segb = wrank + WORDS;                             // [S] rank -> bucket
+    uint16_t *sorted = segb + S;                                // [TILE] local index, ordered by bucket
+    __shared__ uint32_t warp_sum[WARPS];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, last = p.bucket_count - 1;
+
+    for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
+        const bool vec = p.vec && n_tile == TILE;
+        const uint4 *kv = reinterpret_cast<const uint4 *>(p.values + tile_base);
+
+        // first group of keys: in flight during the bin phase
+        Vec16<uint32_t> kq[GROUP];
+        if (vec) {
+            #pragma unroll
+            for (uint32_t i = 0; i < GROUP; ++i) kq[i] = ld_stream<uint32_t>(kv + i * THREADS + tid);
+        }
+        if (tid == 0) {
+            const uint64_t next = (uint64_t) tile + gridDim.x;
+            if (next < p.tiles) {
+                if (p.vec && (next + 1) * TILE <= p.size)
+                    bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
+                bulk_prefetch_l2(p.tile_off + next * S, S * 4);
+                bulk_prefetch_l2(p.tile_cnt + next * S, S * 2);
+            }
+        }
+        for (uint32_t w = tid; w < WORDS; w += THREADS) bitmap[w] = 0;
+        __syncthreads();
+
+        // ---- (1) bins: thread t owns 8 consecutive buckets per round; boundary bits ----------
+        {
+            const uint32_t chunk = tile / p.tiles_per_chunk;
+            const uint16_t *cnt = p.tile_cnt + (size_t) tile * S;
+            const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < S; base += THREADS * 8) {
+                const uint32_t b0 = base + tid * 8;
+                uint32_t c[8], g[8];
+                #pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) { c[j] = 0; g[j] = 0; }
+                if (b0 < S) {
+                    const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(cnt + b0));
+                    const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(toff + b0)),
+                                t1 = __ldg(reinterpret_cast<const uint4 *>(toff + b0 + 4)),
+                                r0 = __ldg(reinterpret_cast<const uint4 *>(crow + b0)),
+                                r1 = __ldg(reinterpret_cast<const uint4 *>(crow + b0 + 4));
+                    uint32_t s8[8];
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) s8[j] = b0 + j < p.bucket_count ? __ldg(p.bucket_start + b0 + j) : 0u;
+                    c[0] = cc.x & 0xffffu; c[1] = cc.x >> 16; c[2] = cc.y & 0xffffu; c[3] = cc.y >> 16;
+                    c[4] = cc.z & 0xffffu; c[5] = cc.z >> 16; c[6] = cc.w & 0xffffu; c[7] = cc.w >> 16;
+                    g[0] = t0.x + r0.x + s8[0]; g[1] = t0.y + r0.y + s8[1]; g[2] = t0.z + r0.z + s8[2]; g[3] = t0.w + r0.w + s8[3];
+                    g[4] = t1.x + r1.x + s8[4]; g[5] = t1.y + r1.y + s8[5]; g[6] = t1.z + r1.z + s8[6]; g[7] = t1.w + r1.w + s8[7];
+                }
+                uint32_t sum = 0;
+                #pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) sum += c[j];
+                uint32_t incl = sum;
+                #pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = shfl_up(incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) warp_sum[warp] = incl;
+                __syncthreads();
+                uint32_t wbase = 0, total = 0;
+                #pragma unroll
+                for (uint32_t w = 0; w < WARPS; ++w) {
+                    if (w == warp) wbase = total;
+                    total += warp_sum[w];
+                }
+                uint32_t run = carry + wbase + incl - sum;
+                carry += total;
+                if (b0 < S) {
+                    uint32_t st[8];
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        st[j] = run; g[j] -= run;
+                        if (c[j]) atomicOr(bitmap + (run >> 5), 1u << (run & 31u));
+                        run += c[j];
+                    }
+                    *reinterpret_cast<uint4 *>(cursor + b0) = make_uint4(st[0], st[1], st[2], st[3]);
+                    *reinterpret_cast<uint4 *>(cursor + b0 + 4) = make_uint4(st[4], st[5], st[6], st[7]);
+                    *reinterpret_cast<uint4 *>(delta + b0) = make_uint4(g[0], g[1], g[2], g[3]);
+                    *reinterpret_cast<uint4 *>(delta + b0 + 4) = make_uint4(g[4], g[5], g[6], g[7]);
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- (2) set bits before every bitmap word (two words per thread) ---------------------
+        {
+            const uint32_t w0 = 2 * tid, w1 = w0 + 1;
+            const uint32_t p0 = w0 < WORDS ? (uint32_t) __popc(bitmap[w0]) : 0u,
+                           p1 = w1 < WORDS ? (uint32_t) __popc(bitmap[w1]) : 0u;
+            uint32_t incl = p0 + p1;
+            #pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const uint32_t t = shfl_up(incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) warp_sum[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            #pragma unroll
+            for (uint32_t w = 0; w < WARPS; ++w)
+                if (w < warp) wbase += warp_sum[w];
+            const uint32_t excl = wbase + incl - p0 - p1;
+            if (w0 < WORDS) wrank[w0] = (uint16_t) excl;
+            if (w1 < WORDS) wrank[w1] = (uint16_t) (excl + p0);
+        }
+        __syncthreads();
+
+        // ---- (3) rank -> bucket, from the untouched cursors ------------------------------------
+        for (uint32_t b = tid; b < S; b += THREADS) {
+            const uint32_t st = cursor[b], en = b + 1 < S ? cursor[b + 1] : n_tile;
+            if (en != st) {
+                const uint32_t r = wrank[st >> 5] + (uint32_t) __popc(bitmap[st >> 5] & ((1u << (st & 31u)) - 1u));
+                segb[r] = (uint16_t) b;
+            }
+        }
+        __syncthreads();
+
+        // ---- (4) ranking: slot from the bucket's cursor, local index stored at the slot ---------
+        if (vec) {
+            #pragma unroll
+            for (uint32_t grp = 0; grp < KPT / (4 * GROUP); ++grp) {
+                Vec16<uint32_t> nx[GROUP];
+                if (grp + 1 < KPT / (4 * GROUP)) {
+                    #pragma unroll
+                    for (uint32_t i = 0; i < GROUP; ++i)
+                        nx[i] = ld_stream<uint32_t>(kv + ((grp + 1) * GROUP + i) * THREADS + tid);
+                }
+                #pragma unroll
+                for (uint32_t i = 0; i < GROUP; ++i) {
+                    const uint32_t local = ((grp * GROUP + i) * THREADS + tid) * 4;
+                    #pragma unroll
+                    for (uint32_t e = 0; e < 4; ++e)
+                        sorted[atomicAdd(cursor + min(kq[i].v[e], last), 1u)] = (uint16_t) (local + e);
+                }
+                #pragma unroll
+                for (uint32_t i = 0; i < GROUP; ++i) kq[i] = nx[i];
+            }
+        } else {
+            for (uint32_t i = tid; i < n_tile; i += THREADS)
+                sorted[atomicAdd(cursor + min(__ldg(p.values + tile_base + i), last), 1u)] = (uint16_t) i;
+        }
+        __syncthreads();
+
+        // ---- (5) copy-out: the bucket of slot j is segb[number of bucket starts <= j, minus 1] ---
+        const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
+        #pragma unroll 4
+        for (uint32_t j = tid; j < n_tile; j += THREADS) {
+            const uint32_t w = j >> 5;
+            const uint32_t r = wrank[w] + (uint32_t) __popc(bitmap[w] & lanemask_le()) - 1u;
+            p.perm[delta[segb[r]] + j] = idx0 + sorted[j];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 //  Stable tile scatter (bucket counts for which the reference guarantees a stable permutation)
 // ---------------------------------------------------------------------------
 //  jit.h:2404-2406: the reference's "tiny" variant -- bucket_count * 4 bytes * 32 warps fit into
@@ -873,9 +1060,11 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
         t.debug = (uint8_t) debug;
     }
 
+    constexpr bool STAGE16 = !STABLE && KPT >= 60;       // 16-bit staging entries (mkperm_tile_scatter16_kernel)
     const uint32_t hist_smem = t.stride * 8,
                    scatter_smem = STABLE ? (THREADS / 32 + 1) * t.stride * 4 + TILE * 4
-                                         : t.stride * 8 + TILE * 4;
+                                : STAGE16 ? t.stride * 10 + TILE / 32 * 6 + TILE * 2
+                                          : t.stride * 8 + TILE * 4;
     uint32_t chunks = std::min(t.tiles, dev.sm_count * 2);
     t.tiles_per_chunk = ceil_div(t.tiles, chunks);
     chunks = ceil_div(t.tiles, t.tiles_per_chunk);
@@ -917,7 +1106,10 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     if (!configured) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));
-        if (!STABLE)
+        if constexpr (STAGE16)
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter16_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int) (dev.smem_optin - 1024)));
+        else if (!STABLE)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4, dev.smem_optin - 1024)));
         configured = true;
@@ -945,7 +1137,10 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     } else {
         const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
         const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
-        mkperm_tile_scatter_kernel<THREADS, KPT><<<grid, THREADS, scatter_smem, stream>>>(t);
+        if constexpr (STAGE16)
+            mkperm_tile_scatter16_kernel<THREADS, KPT><<<std::min(t.tiles, dev.sm_count), THREADS, scatter_smem, stream>>>(t);
+        else
+            mkperm_tile_scatter_kernel<THREADS, KPT><<<grid, THREADS, scatter_smem, stream>>>(t);
     }
     DJB_POST_LAUNCH();
 
@@ -1008,6 +1203,10 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
             return stride * 8 + 1024 * kpt * 4 <= dev.smem_optin - 1024 && size >= dev.sm_count * 2u * 1024u * kpt;
         };
         const uint32_t kpt = kpt_env ? (uint32_t) kpt_env : kMkpermDefaultKpt;
+        // (experimental, only by request: 60 Ki-key tiles with 16-bit staging entries)
+        if (kpt_env == 60 && stride * 10 + 1024 * 60 / 32 * 6 + 1024 * 60 * 2 <= dev.smem_optin - 1024 &&
+            size >= dev.sm_count * 2u * 1024u * 60u)
+            return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
         // (two co-resident 512-thread CTAs with 20 Ki / 16 Ki-key tiles were measured and are slower:
         // 0.396 / 0.499 ms against 0.348 ms, profiles/r2o_mkperm_tile_keys.txt)
         if (kpt >= 48 && fits(48))

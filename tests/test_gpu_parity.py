@@ -585,7 +585,9 @@ def test_mkperm_baseline_config():
 def test_mkperm_unordered_tiles_ragged_unaligned(buckets):
     """unordered tile kernel (beyond the reference's stable range) at sizes where the largest tile
     applies: ragged last tile, input not 16-byte aligned, keys drawn from all / from few buckets"""
-    n = 148 * 2 * 48 * 1024 + 12_345
+    import os
+    kpt = max(48, int(os.environ.get("DRJIT_B200_MKPERM_KPT", "48") or 48))     # (A/B runs of larger tiles)
+    n = 148 * 2 * kpt * 1024 + 12_345
     buf = torch.empty(n + 1, dtype=torch.int32, device="cuda")
     for mis in (0, 1):
         kd = buf[mis:mis + n]
