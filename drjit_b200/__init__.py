@@ -12,9 +12,12 @@ Layers (bottom-up):
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is absent)
 from .ops import (ReduceOp, ReduceMode, VarType, all, any, block_mkperm, block_prefix_reduce,  # noqa: F401,A004
                   block_prefix_sum, block_reduce, block_sum, compress, cumsum, dot, max, min,
-                  prefix_sum, prod, scatter_add, scatter_reduce, sum, launch_count, version)
+                  prefix_sum, prod, scatter_add, scatter_reduce, sum, launch_count, version,
+                  JitFlag, KernelType, set_flag, flag, kernel_history, kernel_history_clear,
+                  reserve_scratch)
 
 __all__ = ["ReduceOp", "ReduceMode", "VarType", "all", "any", "block_mkperm", "block_prefix_reduce",
            "block_prefix_sum", "block_reduce", "block_sum", "compress", "cumsum", "dot", "max",
            "min", "prefix_sum", "prod", "scatter_add", "scatter_reduce", "sum", "launch_count",
-           "version"]
+           "version", "JitFlag", "KernelType", "set_flag", "flag", "kernel_history",
+           "kernel_history_clear", "reserve_scratch"]

@@ -7,7 +7,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdrjit_b200.so")
+# DRJIT_B200_LIB selects another build of the same library (developer tooling: the
+# -DDRJIT_B200_EXPERIMENTS variant that scripts/ use for A/B timing). Never a fallback.
+LIB_PATH = os.environ.get("DRJIT_B200_LIB") or os.path.join(_HERE, "lib", "libdrjit_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -28,6 +30,12 @@ SIGNATURES = {
     "drjit_b200_shutdown": (i32, []),
     "drjit_b200_set_allocator": (i32, [vp, vp, vp]),
     "drjit_b200_launch_count": (u64, [i32]),
+    "drjit_b200_reserve_scratch": (i32, [vp, ctypes.c_size_t]),
+    "drjit_b200_set_launch_hook": (i32, [vp, vp]),
+    "drjit_b200_set_flags": (i32, [u32]),
+    "drjit_b200_flags": (u32, []),
+    "drjit_b200_kernel_history": (u32, [vp, u32]),
+    "drjit_b200_kernel_history_clear": (None, []),
     "drjit_b200_memset_async": (i32, [vp, vp, u32, u32, vp]),
     "drjit_b200_block_reduce": (i32, [vp, i32, i32, u32, u32, vp, vp]),
     "drjit_b200_block_reduce_bool": (i32, [vp, vp, u32, vp, i32]),
@@ -44,6 +52,22 @@ SIGNATURES = {
     "drjit_b200_compress_async": (i32, [vp, vp, u32, u32, vp, vp]),
     "drjit_b200_mkperm_sharded": (i32, [vp, vp, u32, u32, u32, vp, vp]),
     "drjit_b200_fill_fmix32": (i32, [vp, i32, vp, u64, u64, u32, u32]),
+    # multi-GPU forms (peer-memory communicator)
+    "drjit_b200_comm_create": (i32, [u32, u32, ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "drjit_b200_comm_handle": (i32, [vp, vp]),
+    "drjit_b200_comm_connect": (i32, [vp, vp]),
+    "drjit_b200_comm_connect_local": (i32, [ctypes.POINTER(vp), u32]),
+    "drjit_b200_comm_destroy": (i32, [vp]),
+    "drjit_b200_comm_reduce": (i32, [vp, vp, i32, i32, i32, u32, vp, vp]),
+    "drjit_b200_comm_reduce_dot": (i32, [vp, vp, i32, vp, vp, u32, vp]),
+    "drjit_b200_comm_all": (i32, [vp, vp, vp, u32, pint]),
+    "drjit_b200_comm_any": (i32, [vp, vp, vp, u32, pint]),
+    "drjit_b200_comm_prefix_reduce": (i32, [vp, vp, i32, i32, u32, i32, i32, vp, vp, vp, i32]),
+    "drjit_b200_comm_compress": (i32, [vp, vp, vp, u32, u32, vp, pu32]),
+    "drjit_b200_comm_mkperm": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp, pu32]),
+    "drjit_b200_comm_allreduce": (i32, [vp, vp, i32, i32, vp, u32]),
+    "drjit_b200_comm_allgather": (i32, [vp, vp, vp, u32, vp]),
+    "drjit_b200_comm_fold": (i32, [vp, vp, i32, i32, i32, vp, vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

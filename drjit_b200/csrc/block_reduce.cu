@@ -17,6 +17,7 @@
  *    deterministic; the reference recurses with 2-3 launches and temp buffers (:347-351).
  */
 #include "common.cuh"
+#include "comm.cuh"
 #include "runtime.h"
 
 namespace djb {
@@ -278,12 +279,15 @@ template <typename T, typename Op, bool DOT> struct ChunkAccum {
     }
 };
 
-template <typename T, typename Op, bool DOT, bool VEC>
+/// PEER (full reductions of a shard): the CTA that holds the shard's result
+/// exchanges it with the other ranks of the communicator through peer memory and folds the W
+/// values in rank order before it stores `out` (comm.cuh) -- reduction + combine in one launch.
+template <typename T, typename Op, bool DOT, bool VEC, bool PEER = false>
 __global__ void __launch_bounds__(kThreads)
 block_reduce_chunk_kernel(const T *__restrict__ in, const T *__restrict__ in2, T *__restrict__ out,
                           acc_t<T> *__restrict__ partials, uint32_t *__restrict__ counters,
                           uint32_t size, uint32_t block_size, uint32_t chunk_elems,
-                          uint32_t chunks_per_block) {
+                          uint32_t chunks_per_block, const PeerCtx peer = PeerCtx{}, uint32_t fold = 0) {
     using A = acc_t<T>;
     using Acc = ChunkAccum<T, Op, DOT>;
     constexpr uint32_t V = 16 / sizeof(T);
@@ -363,7 +367,10 @@ block_reduce_chunk_kernel(const T *__restrict__ in, const T *__restrict__ in2, T
     A total = block_reduce<Comb, A, kThreads>(acc, smem, ident);
 
     if (chunks_per_block == 1) {
-        if (tid == 0) out[block] = from_acc<T>(total);
+        if (tid == 0) {
+            if constexpr (PEER) total = peer_fold_scalar<Comb, A>(peer, total, fold);
+            out[block] = from_acc<T>(total);
+        }
         return;
     }
 
@@ -386,8 +393,9 @@ block_reduce_chunk_kernel(const T *__restrict__ in, const T *__restrict__ in2, T
     __syncthreads(); // smem reuse
     total = block_reduce<Comb, A, kThreads>(acc, smem, ident);
     if (tid == 0) {
-        out[block] = from_acc<T>(total);
         counters[block] = 0; // leave the control block zeroed for the next call
+        if constexpr (PEER) total = peer_fold_scalar<Comb, A>(peer, total, fold);
+        out[block] = from_acc<T>(total);
     }
 }
 
@@ -398,12 +406,37 @@ constexpr uint32_t kGroupMaxBytes = 4096;     // blocks up to this size use the 
 constexpr uint32_t kMinChunkBytes = 32768;    // never split a block into chunks smaller than this
 constexpr uint32_t kCtasPerSm = 8;
 
+/// Full reduction of a shard + combine over the ranks of a communicator in ONE launch: the chunk
+/// kernel over the whole shard (any size, including an empty trailing shard, which contributes the
+/// identity), PEER tail.
+template <typename T, typename Op>
+static void launch_reduce_peer(cudaStream_t stream, const PeerCtx &peer, uint32_t fold, uint32_t size,
+                               const T *in, T *out) {
+    using A = acc_t<T>;
+    constexpr uint32_t V = 16 / sizeof(T);
+    const DeviceProps &dev = device_props();
+    const uint32_t quantum = kThreads * V * 4;
+    const uint64_t bytes = (uint64_t) size * sizeof(T);
+    uint32_t cpb = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(dev.sm_count * kCtasPerSm, bytes / kMinChunkBytes));
+    uint32_t chunk_elems = std::max(quantum, ceil_div(ceil_div(size, cpb), quantum) * quantum);
+    cpb = std::max(1u, ceil_div(size, chunk_elems));
+    Scratch scratch(stream);
+    A *partials = cpb > 1 ? (A *) scratch.device((size_t) cpb * sizeof(A)) : nullptr;
+    block_reduce_chunk_kernel<T, Op, false, true, true><<<cpb, kThreads, 0, stream>>>(
+        in, nullptr, out, partials, scratch.zeroed_counters(), size, std::max(size, 1u), chunk_elems, cpb, peer, fold);
+    DJB_POST_LAUNCH();
+}
+
 template <typename T, typename Op>
 static void launch_block_reduce(cudaStream_t stream, uint32_t size, uint32_t block_size,
-                                const void *in_, void *out_) {
+                                const void *in_, void *out_, const PeerCtx *peer = nullptr, uint32_t fold = 0) {
     using A = acc_t<T>;
     const T *in = (const T *) in_;
     T *out = (T *) out_;
+    if (peer) {
+        launch_reduce_peer<T, Op>(stream, *peer, fold, size, in, out);
+        return;
+    }
     const DeviceProps &dev = device_props();
     const uint32_t block_count = ceil_div(size, block_size);
     const uint64_t block_bytes = (uint64_t) block_size * sizeof(T);
@@ -483,34 +516,37 @@ static void launch_block_reduce(cudaStream_t stream, uint32_t size, uint32_t blo
 }
 
 template <typename T> static void dispatch_op_int(cudaStream_t s, int op, uint32_t size,
-                                                  uint32_t bs, const void *in, void *out) {
+                                                  uint32_t bs, const void *in, void *out,
+        const PeerCtx *peer = nullptr, uint32_t fold = 0) {
     switch (op) {
-        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_AND: launch_block_reduce<T, OpAnd>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_OR:  launch_block_reduce<T, OpOr>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_AND: launch_block_reduce<T, OpAnd>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_OR:  launch_block_reduce<T, OpOr>(s, size, bs, in, out, peer, fold); break;
         default: raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): unsupported reduction type!");
     }
 }
 
 template <typename T> static void dispatch_op_minmax(cudaStream_t s, int op, uint32_t size,
-                                                     uint32_t bs, const void *in, void *out) {
+                                                     uint32_t bs, const void *in, void *out,
+        const PeerCtx *peer = nullptr, uint32_t fold = 0) {
     switch (op) {
-        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out, peer, fold); break;
         default: raise(DRJIT_B200_EFATAL, "jit_block_reduce(): internal dispatch error");
     }
 }
 
 template <typename T> static void dispatch_op_float(cudaStream_t s, int vt, int op, uint32_t size,
-                                                    uint32_t bs, const void *in, void *out) {
+                                                    uint32_t bs, const void *in, void *out,
+        const PeerCtx *peer = nullptr, uint32_t fold = 0) {
     switch (op) {
-        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out); break;
-        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out); break;
+        case DRJIT_B200_OP_ADD: launch_block_reduce<T, OpAdd>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MUL: launch_block_reduce<T, OpMul>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MIN: launch_block_reduce<T, OpMin>(s, size, bs, in, out, peer, fold); break;
+        case DRJIT_B200_OP_MAX: launch_block_reduce<T, OpMax>(s, size, bs, in, out, peer, fold); break;
         default:
             // wording of cuda_ts.cpp:313-315
             raise(DRJIT_B200_EUNSUPPORTED,
@@ -518,6 +554,34 @@ template <typename T> static void dispatch_op_float(cudaStream_t s, int vt, int 
                   op_name(op));
     }
 }
+
+static void dispatch_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uint32_t block_size,
+                            const void *in, void *out, const PeerCtx *peer, uint32_t fold) {
+    // Signed sum/product/and/or reductions can use the unsigned kernel (cuda_ts.cpp:215-225)
+    const bool sign_agnostic = op == DRJIT_B200_OP_ADD || op == DRJIT_B200_OP_MUL ||
+                               op == DRJIT_B200_OP_AND || op == DRJIT_B200_OP_OR;
+    switch (vt) {
+        case DRJIT_B200_VT_BOOL:
+        case DRJIT_B200_VT_UINT8:  dispatch_op_int<uint8_t>(stream, op, size, block_size, in, out, peer, fold); break;
+        case DRJIT_B200_VT_UINT32: dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out, peer, fold); break;
+        case DRJIT_B200_VT_UINT64: dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out, peer, fold); break;
+        case DRJIT_B200_VT_INT32:
+            if (sign_agnostic) dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out, peer, fold);
+            else dispatch_op_minmax<int32_t>(stream, op, size, block_size, in, out, peer, fold);
+            break;
+        case DRJIT_B200_VT_INT64:
+            if (sign_agnostic) dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out, peer, fold);
+            else dispatch_op_minmax<int64_t>(stream, op, size, block_size, in, out, peer, fold);
+            break;
+        case DRJIT_B200_VT_FLOAT16: dispatch_op_float<__half>(stream, vt, op, size, block_size, in, out, peer, fold); break;
+        case DRJIT_B200_VT_FLOAT32: dispatch_op_float<float>(stream, vt, op, size, block_size, in, out, peer, fold); break;
+        case DRJIT_B200_VT_FLOAT64: dispatch_op_float<double>(stream, vt, op, size, block_size, in, out, peer, fold); break;
+        default:
+            raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): no existing kernel for type=%s, op=%s!",
+                  type_name(vt), op_name(op));
+    }
+}
+
 
 void block_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uint32_t block_size,
                   const void *in, void *out) {
@@ -538,29 +602,18 @@ void block_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uint32_t b
         return;
     }
 
-    // Signed sum/product/and/or reductions can use the unsigned kernel (cuda_ts.cpp:215-225)
-    const bool sign_agnostic = op == DRJIT_B200_OP_ADD || op == DRJIT_B200_OP_MUL ||
-                               op == DRJIT_B200_OP_AND || op == DRJIT_B200_OP_OR;
-    switch (vt) {
-        case DRJIT_B200_VT_BOOL:
-        case DRJIT_B200_VT_UINT8:  dispatch_op_int<uint8_t>(stream, op, size, block_size, in, out); break;
-        case DRJIT_B200_VT_UINT32: dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out); break;
-        case DRJIT_B200_VT_UINT64: dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out); break;
-        case DRJIT_B200_VT_INT32:
-            if (sign_agnostic) dispatch_op_int<uint32_t>(stream, op, size, block_size, in, out);
-            else dispatch_op_minmax<int32_t>(stream, op, size, block_size, in, out);
-            break;
-        case DRJIT_B200_VT_INT64:
-            if (sign_agnostic) dispatch_op_int<uint64_t>(stream, op, size, block_size, in, out);
-            else dispatch_op_minmax<int64_t>(stream, op, size, block_size, in, out);
-            break;
-        case DRJIT_B200_VT_FLOAT16: dispatch_op_float<__half>(stream, vt, op, size, block_size, in, out); break;
-        case DRJIT_B200_VT_FLOAT32: dispatch_op_float<float>(stream, vt, op, size, block_size, in, out); break;
-        case DRJIT_B200_VT_FLOAT64: dispatch_op_float<double>(stream, vt, op, size, block_size, in, out); break;
-        default:
-            raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): no existing kernel for type=%s, op=%s!",
-                  type_name(vt), op_name(op));
-    }
+    dispatch_reduce(stream, vt, op, size, block_size, in, out, nullptr, 0);
+}
+
+/// Full reduction of this rank's shard fused with the combine over all ranks (one launch): every
+/// rank's `out[0]` receives the fold selected by `fold` (PeerFold). size == 0 is a valid (empty) shard.
+void comm_reduce(cudaStream_t stream, const Comm *comm, int vt, int op, uint32_t fold, uint32_t size,
+                 const void *in, void *out) {
+    const PeerCtx peer = comm_ctx(comm);
+    if (type_size(vt) == 0 || op < DRJIT_B200_OP_ADD || op > DRJIT_B200_OP_OR || fold > kFoldHigher)
+        raise(DRJIT_B200_EUNSUPPORTED, "jit_block_reduce(): no existing kernel for type=%s, op=%s!",
+              type_name(vt), op_name(op));
+    dispatch_reduce(stream, vt, op, size, std::max(size, 1u), in, out, &peer, fold);
 }
 
 // ---------------------------------------------------------------------------
@@ -666,6 +719,7 @@ bool all_any(cudaStream_t stream, const uint8_t *values, uint32_t size, int op) 
     uint8_t *dev_view = nullptr;
     DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &dev_view, pinned, 0));
     launch_reduce_bool(stream, scratch, values, size, dev_view, op);
+    scratch.unlock();                                      // (never block on the GPU with the stream's lock held)
     DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
     const uint8_t *b = reinterpret_cast<const uint8_t *>(pinned);
     // util.cpp:191,207: combine the four packed partials
@@ -676,7 +730,8 @@ bool all_any(cudaStream_t stream, const uint8_t *values, uint32_t size, int op) 
 //  Dot product
 // ---------------------------------------------------------------------------
 template <typename T>
-static void launch_reduce_dot(cudaStream_t stream, const void *a_, const void *b_, uint32_t size, void *out_) {
+static void launch_reduce_dot(cudaStream_t stream, const void *a_, const void *b_, uint32_t size, void *out_,
+                              const PeerCtx *peer = nullptr) {
     using A = acc_t<T>;
     constexpr uint32_t V = 16 / sizeof(T);
     const T *a = (const T *) a_, *b = (const T *) b_;
@@ -688,15 +743,21 @@ static void launch_reduce_dot(cudaStream_t stream, const void *a_, const void *b
     const uint32_t max_cpb = (uint32_t) std::max<uint64_t>(1, bytes / (kMinChunkBytes / 2));
     if (cpb > max_cpb) cpb = max_cpb;
     const uint32_t quantum = kThreads * V * 4;
-    uint32_t chunk_elems = ceil_div(ceil_div(size, cpb), quantum) * quantum;
-    cpb = ceil_div(size, chunk_elems);
+    uint32_t chunk_elems = std::max(quantum, ceil_div(ceil_div(size, cpb), quantum) * quantum);
+    cpb = std::max(1u, ceil_div(size, chunk_elems));
 
     Scratch scratch(stream);
     A *partials = cpb > 1 ? (A *) scratch.device((size_t) cpb * sizeof(A)) : nullptr;
     uint32_t *counters = scratch.zeroed_counters();
     // both streams must share their misalignment for the 128-bit path
     const bool vec = (((uintptr_t) a ^ (uintptr_t) b) & 15) == 0;
-    if (vec)
+    if (peer && vec)        // shard of a sharded dot product: combine over the ranks in the same launch
+        block_reduce_chunk_kernel<T, OpAdd, true, true, true><<<cpb, kThreads, 0, stream>>>(
+            a, b, out, partials, counters, size, std::max(size, 1u), chunk_elems, cpb, *peer, kFoldAll);
+    else if (peer)
+        block_reduce_chunk_kernel<T, OpAdd, true, false, true><<<cpb, kThreads, 0, stream>>>(
+            a, b, out, partials, counters, size, std::max(size, 1u), chunk_elems, cpb, *peer, kFoldAll);
+    else if (vec)
         block_reduce_chunk_kernel<T, OpAdd, true, true><<<cpb, kThreads, 0, stream>>>(
             a, b, out, partials, counters, size, size, chunk_elems, cpb);
     else
@@ -718,6 +779,38 @@ void reduce_dot(cudaStream_t stream, int vt, const void *a, const void *b, uint3
         case DRJIT_B200_VT_FLOAT32: launch_reduce_dot<float>(stream, a, b, size, out); break;
         default: launch_reduce_dot<double>(stream, a, b, size, out); break;
     }
+}
+
+/// Dot product of this rank's shards fused with the sum over all ranks (one launch)
+void comm_reduce_dot(cudaStream_t stream, const Comm *comm, int vt, const void *a, const void *b, uint32_t size,
+                     void *out) {
+    const PeerCtx peer = comm_ctx(comm);
+    switch (vt) {
+        case DRJIT_B200_VT_FLOAT16: launch_reduce_dot<__half>(stream, a, b, size, out, &peer); break;
+        case DRJIT_B200_VT_FLOAT32: launch_reduce_dot<float>(stream, a, b, size, out, &peer); break;
+        case DRJIT_B200_VT_FLOAT64: launch_reduce_dot<double>(stream, a, b, size, out, &peer); break;
+        default: raise(DRJIT_B200_EUNSUPPORTED, "jit_reduce_dot(): no existing kernel for type=%s!", type_name(vt));
+    }
+}
+
+/// dr.all / dr.any over a sharded mask (synchronous like jitc_all/any): local packed flag, scalar
+/// And/Or fold over the ranks through peer memory straight into a pinned word, one wait.
+bool comm_all_any(cudaStream_t stream, const Comm *comm, const uint8_t *values, uint32_t size, int op) {
+    (void) comm_ctx(comm);      // validates
+    Scratch scratch(stream);
+    uint32_t *pinned = scratch.pinned_words();
+    uint32_t *dev_view = nullptr;
+    DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &dev_view, pinned, 0));
+    uint32_t *local = (uint32_t *) scratch.device(256);
+    if (size == 0)              // empty trailing shard: identity
+        DJB_CUDA_CHECK(cudaMemsetAsync(local, op == DRJIT_B200_OP_AND ? 0xff : 0, 4, stream));
+    else
+        launch_reduce_bool(stream, scratch, values, size, (uint8_t *) local, op);
+    comm_fold_scalar(stream, comm, DRJIT_B200_VT_UINT32, op, kFoldAll, local, dev_view);
+    scratch.unlock();
+    DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(pinned);
+    return op == DRJIT_B200_OP_AND ? (b[0] & b[1] & b[2] & b[3]) != 0 : (b[0] | b[1] | b[2] | b[3]) != 0;
 }
 
 } // namespace djb

@@ -15,6 +15,15 @@
 #  error "drjit_b200 kernels target sm_100a (B200) only"
 #endif
 
+// Timing experiments (phases of a kernel switched off, alternative tile sizes, ...) exist only in
+// builds with -DDRJIT_B200_EXPERIMENTS (scripts/ and `make EXPERIMENTS=1`). In the shipped library
+// every DJB_DEBUG(...) is the constant 0 and no environment variable is read on the product path.
+#if defined(DRJIT_B200_EXPERIMENTS)
+#  define DJB_DEBUG(expr) (expr)
+#else
+#  define DJB_DEBUG(expr) 0u
+#endif
+
 namespace djb {
 
 constexpr uint32_t kWarp = 32;

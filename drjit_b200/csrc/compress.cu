@@ -14,6 +14,7 @@
 #include "compress_kernel.cuh"
 #include "runtime.h"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace djb {
@@ -27,13 +28,14 @@ static void launch_compress(cudaStream_t stream, CompressParams &p, Scratch &scr
     auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * TILE;
     // (function attributes and occupancy are per device: one slot per device and instantiation)
-    static int occupancy_of[kMaxDevices] = {};
-    int &occupancy = occupancy_of[dev.device % kMaxDevices];
-    if (occupancy == 0) {
+    static std::atomic<int> occupancy_of[kMaxDevices] = {};
+    int occupancy = occupancy_of[dev.device % kMaxDevices].load(std::memory_order_acquire);
+    if (occupancy == 0) {                                   // (idempotent: a race only repeats the queries)
         if (smem > 48 * 1024)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         DJB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, kCompThreads, smem));
         if (occupancy < 1) occupancy = 1;
+        occupancy_of[dev.device % kMaxDevices].store(occupancy, std::memory_order_release);
     }
     p.tiles = ceil_div(p.size, TILE);
     const size_t state_bytes = (size_t) p.tiles * 8;
@@ -87,8 +89,29 @@ uint32_t compress(cudaStream_t stream, const uint8_t *in, uint32_t size, uint32_
     if (count_dev) {
         DJB_CUDA_CHECK(cudaMemcpyAsync(pinned, count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     }
+    scratch.unlock();                                      // (never block on the GPU with the stream's lock held)
     DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
     return pinned[0];
+}
+
+/// Compaction of this rank's shard of a global mask (indices are global: index_base + local) fused
+/// with the exchange of the per-rank counts: counts_host[0..world) (host memory) receives every
+/// rank's count, so rank r's list starts at sum(counts_host[0..r)) of the rank-major global list.
+/// Synchronous like the reference (cuda_ts.cpp:759): one wait, no library collective.
+void comm_compress(cudaStream_t stream, const Comm *comm, const uint8_t *in, uint32_t size, uint32_t index_base,
+                   uint32_t *out, uint32_t *counts_host) {
+    const uint32_t world = comm_world(comm);
+    Scratch scratch(stream);
+    static_assert(Scratch::kPinnedSlotWords >= 8, "one pinned word per rank");
+    uint32_t *count_dev = (uint32_t *) scratch.device(256);
+    uint32_t *pinned = scratch.pinned_words(), *pinned_dev = nullptr;
+    DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &pinned_dev, pinned, 0));
+    compress(stream, in, size, index_base, out, count_dev, false);
+    comm_allgather(stream, comm, count_dev, 4, pinned_dev);     // the exchange kernel writes the W counts to the host
+    scratch.unlock();
+    DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (uint32_t r = 0; r < world; ++r)
+        counts_host[r] = pinned[r];
 }
 
 } // namespace djb

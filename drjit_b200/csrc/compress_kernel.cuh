@@ -43,7 +43,7 @@ struct CompressParams {
     uint64_t *state;      // tile descriptors {count << 32 | kCAggregate}, zero on entry
     uint32_t *count_out;  // device-accessible
     uint32_t size, tiles, index_base;
-    uint32_t debug;       // timing experiments only (scripts/sweep_compress.cu): 1 = carry chain disabled
+    uint32_t debug;       // read only in -DDRJIT_B200_EXPERIMENTS builds (scripts/sweep_compress.cu): 1 = carry chain disabled
 };
 
 constexpr uint32_t kCompWindowLoads = 3;                     // carry window: grids of up to 768 CTAs
@@ -209,7 +209,7 @@ compress_kernel(const CompressParams p) {
         // ---- carry window: counts of the tiles between this CTA's previous tile and this one ----
         // (scan_kernel.cuh, "WINDOW")
         uint64_t wd[kCompWindowLoads];
-        const uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x, win_n = (p.debug & 1u) ? 0u : tile - win_lo;
+        const uint32_t win_lo = it == 0 ? 0u : tile - gridDim.x, win_n = (DJB_DEBUG(p.debug) & 1u) ? 0u : tile - win_lo;
         #pragma unroll
         for (uint32_t j = 0; j < kCompWindowLoads; ++j) {
             const uint32_t o = j * kCompThreads + tid;
@@ -238,7 +238,7 @@ compress_kernel(const CompressParams p) {
         #pragma unroll
         for (uint32_t w = 0; w < kCompWarps; ++w)
             carry += win_cnt[it & 1u][w];
-        if (p.debug & 1u) carry = tile * (TILE / 2);       // (keeps the write stream spread out)
+        if (DJB_DEBUG(p.debug) & 1u) carry = tile * (TILE / 2);       // (keeps the write stream spread out)
         if (tile == p.tiles - 1 && tid == 0) {
             uint32_t ttotal = 0;
             #pragma unroll

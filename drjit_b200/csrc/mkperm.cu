@@ -25,9 +25,11 @@
  *   GLOBAL : global-memory atomics for bucket counts beyond shared memory ("large").
  */
 #include "common.cuh"
+#include "comm.cuh"
 #include "tma.cuh"
 #include "runtime.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -70,6 +72,9 @@ __global__ void mkperm_histogram_kernel(const MkpermParams p) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, nwarps = blockDim.x >> 5;
     const uint32_t group = blockIdx.x / p.ctas_per_group, cta = blockIdx.x - group * p.ctas_per_group;
     const uint32_t B = p.bucket_count;
+    // Out-of-range keys (>= bucket_count; undefined behaviour in the reference) are counted in the
+    // last bucket on every path of this file: one policy, no out-of-bounds counter access.
+    const uint32_t last = B - 1;
 
     uint32_t *hist;         // counters this thread adds to
     uint32_t row_in_group;  // slice this warp reads
@@ -107,14 +112,14 @@ __global__ void mkperm_histogram_kernel(const MkpermParams p) {
             for (int u = 0; u < 4; ++u)
                 if (ok[u]) {
                     #pragma unroll
-                    for (int e = 0; e < 4; ++e) atomicAdd(hist + t[u].v[e], 1u);
+                    for (int e = 0; e < 4; ++e) atomicAdd(hist + min(t[u].v[e], last), 1u);
                 }
         }
         for (uint64_t i = start + nvec * 4 + lane; i < end; i += 32)
-            atomicAdd(hist + p.values[i], 1u);
+            atomicAdd(hist + min(p.values[i], last), 1u);
     } else {
         for (uint64_t i = start + lane; i < end; i += 32)
-            atomicAdd(hist + __ldg(p.values + i), 1u);
+            atomicAdd(hist + min(__ldg(p.values + i), last), 1u);
     }
 
     if constexpr (Mode == MkpermMode::Warp) {
@@ -190,54 +195,95 @@ mkperm_column_scan_kernel(const MkpermParams p, uint32_t tiles_per_group) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kBucketScanThreads = 1024;
 
+/// PEER (one sorting group sharded over the ranks of a communicator): the
+/// kernel first exchanges the shard histograms through peer memory (comm.cuh). The table of
+/// non-empty buckets then describes the GLOBAL array (start / size over all ranks, identical on
+/// every rank), rank_base[b] is where this rank's keys of bucket b begin in the global, rank-major
+/// stable order, while `totals` still receives the shard-local bucket starts the scatter pass needs.
+template <bool PEER>
 __global__ void __launch_bounds__(kBucketScanThreads)
 mkperm_bucket_scan_kernel(const MkpermParams p, uint32_t *offsets, uint32_t *unique_out,
-                          uint32_t *hist_out) {
-    __shared__ uint32_t warp_sum[32], warp_uniq[32];
-    __shared__ uint32_t carry_sum, carry_uniq;
+                          uint32_t *hist_out, const PeerCtx peer, uint32_t *rank_base) {
+    __shared__ uint32_t warp_sum[32], warp_uniq[32], warp_gsum[32];
+    __shared__ uint32_t carry_sum, carry_uniq, carry_gsum, epoch_smem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t group = blockIdx.x, B = p.bucket_count;
     uint32_t *totals = p.totals + (size_t) group * B;
 
-    if (tid == 0) { carry_sum = 0; carry_uniq = 0; }
+    if (tid == 0) { carry_sum = 0; carry_uniq = 0; carry_gsum = 0; if (PEER) epoch_smem = peer_begin(peer); }
     __syncthreads();
+    uint32_t epoch = 0;
+    if constexpr (PEER) {
+        epoch = epoch_smem;
+        peer_put_cta(peer, epoch, totals, B * 4);
+        peer_wait_cta(peer, epoch);
+    }
 
     for (uint32_t base = 0; base < B; base += kBucketScanThreads) {
         const uint32_t b = base + tid;
-        const uint32_t n = b < B ? totals[b] : 0u, u = n != 0;
+        const uint32_t n = b < B ? totals[b] : 0u;
+        uint32_t gn = n, before = 0;        // bucket size over all ranks / over the ranks below mine
+        if constexpr (PEER) {
+            gn = 0;
+            if (b < B) {
+                for (uint32_t r = 0; r < peer.world; ++r) {
+                    const uint32_t c = __ldcg(reinterpret_cast<const uint32_t *>(win_slot(peer, peer.rank, epoch, r)) + b);
+                    if (r == peer.rank) before = gn;
+                    gn += c;
+                }
+            }
+        }
+        const uint32_t u = gn != 0;
         if (hist_out && b < B) hist_out[b] = n;
 
-        uint32_t vs = n, vu = u;
+        uint32_t vs = n, vu = u, vg = gn;
         #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) {
-            const uint32_t ts = shfl_up(vs, d), tu = shfl_up(vu, d);
-            if (lane >= d) { vs += ts; vu += tu; }
+            const uint32_t ts = shfl_up(vs, d), tu = shfl_up(vu, d), tg = shfl_up(vg, d);
+            if (lane >= d) { vs += ts; vu += tu; vg += tg; }
         }
-        if (lane == 31) { warp_sum[warp] = vs; warp_uniq[warp] = vu; }
+        if (lane == 31) { warp_sum[warp] = vs; warp_uniq[warp] = vu; warp_gsum[warp] = vg; }
         __syncthreads();
-        uint32_t ws = 0, wu = 0, ts_all = 0, tu_all = 0;
+        uint32_t ws = 0, wu = 0, wg = 0, ts_all = 0, tu_all = 0, tg_all = 0;
         #pragma unroll
         for (uint32_t w = 0; w < 32; ++w) {
-            if (w == warp) { ws = ts_all; wu = tu_all; }
-            ts_all += warp_sum[w]; tu_all += warp_uniq[w];
+            if (w == warp) { ws = ts_all; wu = tu_all; wg = tg_all; }
+            ts_all += warp_sum[w]; tu_all += warp_uniq[w]; tg_all += warp_gsum[w];
         }
-        const uint32_t start = carry_sum + ws + vs - n,   // exclusive
+        const uint32_t start = carry_sum + ws + vs - n,   // exclusive, shard-local
+                       gstart = PEER ? carry_gsum + wg + vg - gn : start,
                        slot = carry_uniq + wu + vu - u;
         if (b < B) {
             totals[b] = start;
+            if (PEER && rank_base) rank_base[b] = gstart + before;
             if (offsets && u) {       // quadruple layout: jit.h:2412-2419, mkperm.cuh:271-320
-                uint4 q = make_uint4(b, start, n, 0u);
+                uint4 q = make_uint4(b, gstart, gn, 0u);
                 *reinterpret_cast<uint4 *>(offsets + 4 * (size_t) slot) = q;
             }
         }
         __syncthreads();
-        if (tid == 0) { carry_sum += ts_all; carry_uniq += tu_all; }
+        if (tid == 0) { carry_sum += ts_all; carry_uniq += tu_all; carry_gsum += tg_all; }
         __syncthreads();
     }
     if (tid == 0 && offsets) {
         offsets[4 * (size_t) B] = carry_uniq;  // cuda_ts.cpp:948-951
         if (unique_out) *unique_out = carry_uniq;
     }
+    if (PEER && tid == 0)
+        peer_end(peer, epoch);
+}
+
+/// Sharded call: communicator view + optional output of this rank's start inside every global bucket
+struct MkpermPeer { PeerCtx ctx; uint32_t *rank_base; };
+
+/// Launches the bucket scan of `p` (PEER when a communicator is given)
+static void launch_bucket_scan(cudaStream_t stream, const MkpermParams &p, uint32_t *offsets_dev, uint32_t *unique_dev,
+                               uint32_t *hist_out, const MkpermPeer *peer) {
+    if (peer)
+        mkperm_bucket_scan_kernel<true><<<p.n_groups, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out, peer->ctx, peer->rank_base);
+    else
+        mkperm_bucket_scan_kernel<false><<<p.n_groups, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out, PeerCtx{}, nullptr);
+    DJB_POST_LAUNCH();
 }
 
 // ---------------------------------------------------------------------------
@@ -248,7 +294,7 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
     extern __shared__ uint32_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, nwarps = blockDim.x >> 5;
     const uint32_t group = blockIdx.x / p.ctas_per_group, cta = blockIdx.x - group * p.ctas_per_group;
-    const uint32_t B = p.bucket_count;
+    const uint32_t B = p.bucket_count, last = B - 1;    // (out-of-range keys: last bucket, as in the histogram)
     const uint32_t group_start = group * p.block_size;   // < size, fits
     const uint32_t *bucket_start = p.totals + (size_t) group * B;
     const uint32_t row_in_group = cta * nwarps + warp;
@@ -280,7 +326,7 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
             for (int u = 0; u < 4; ++u) {
                 const uint64_t i = base + u * 32 + lane;
                 ok[u] = i < end;
-                key[u] = ok[u] ? __ldg(p.values + i) : 0u;
+                key[u] = ok[u] ? min(__ldg(p.values + i), last) : 0u;
             }
             #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -306,7 +352,7 @@ __global__ void mkperm_scatter_kernel(const MkpermParams p) {
         }
     } else {
         auto place = [&](uint32_t key, uint32_t i) {
-            uint32_t pos = atomicAdd(ctr + key, 1u);
+            uint32_t pos = atomicAdd(ctr + min(key, last), 1u);
             if constexpr (Mode == MkpermMode::Global) pos += group_start;
             p.perm[pos] = p.index_base + i;
         };
@@ -379,7 +425,7 @@ struct MkpermTileParams {
     const uint32_t *bucket_start; // [buckets] after the bucket scan
     uint32_t size, bucket_count, stride, tiles, tiles_per_chunk, index_base;
     uint8_t vec;
-    uint8_t debug;           // timing experiments only (DRJIT_B200_MKPERM_DEBUG; results are wrong when set):
+    uint8_t debug;           // read only in -DDRJIT_B200_EXPERIMENTS builds (phases switched off for timing):
                              // 1 = copy-out without its global stores, 2 = no copy-out, 4 = no ranking, 8 = no bucket rows
 };
 
@@ -528,7 +574,7 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         }
 
         // ---- (1) bins: thread t owns 8 consecutive buckets per round ----------------------
-        if (!(p.debug & 8u)) {
+        if (!(DJB_DEBUG(p.debug) & 8u)) {
             const uint32_t chunk = tile / p.tiles_per_chunk;
             const uint16_t *cnt = p.tile_cnt + (size_t) tile * S;
             const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
@@ -585,7 +631,7 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         }
 
         // ---- (2) keys: slot from the bucket's cursor, entry stored at the slot ---------------
-        if (!(p.debug & 4u)) {
+        if (!(DJB_DEBUG(p.debug) & 4u)) {
             #pragma unroll
             for (uint32_t k = 0; k < KPT; ++k) {
                 const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
@@ -608,13 +654,13 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        if (!p.debug) {
+        if (!DJB_DEBUG(p.debug)) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];
                 p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
             }
-        } else if (p.debug == 1u) {
+        } else if (DJB_DEBUG(p.debug) == 1u) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];
@@ -626,6 +672,7 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
     }
 }
 
+#if defined(DRJIT_B200_EXPERIMENTS)
 // ---------------------------------------------------------------------------
 //  Unordered tile scatter with 16-bit staging entries (EXPERIMENTAL: DRJIT_B200_MKPERM_KPT=60)
 // ---------------------------------------------------------------------------
@@ -636,9 +683,8 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 //  count per bitmap word, and a table rank -> bucket. A warp copies 32 aligned slots, so the bitmap
 //  word and the prefix count are warp-uniform loads and the rank is one popcount.
 //  Keys are not held in registers: they are ranked in groups of 20 per thread (5 x LDG.128).
-//  Written after the GPU budget of round 1 was spent: compiles, selected only by the environment
-//  variable above, not yet run on hardware (tests/test_gpu_parity.py -k mkperm with that variable
-//  set is the acceptance test).
+//  Compiled only with -DDRJIT_B200_EXPERIMENTS and selected only by the environment variable above
+//  (scripts/gpu_mkperm_kpt.sh is its acceptance run); not part of the shipped library.
 template <uint32_t THREADS, uint32_t KPT>
 __global__ void __launch_bounds__(THREADS, 1)
 mkperm_tile_scatter16_kernel(const MkpermTileParams p) {
@@ -813,6 +859,8 @@ mkperm_tile_scatter16_kernel(const MkpermTileParams p) {
     }
 }
 
+#endif // DRJIT_B200_EXPERIMENTS
+
 // ---------------------------------------------------------------------------
 //  Stable tile scatter (bucket counts for which the reference guarantees a stable permutation)
 // ---------------------------------------------------------------------------
@@ -967,19 +1015,21 @@ static MkpermMode pick_mode(uint32_t bucket_count, uint32_t smem_budget, uint32_
     else if (bytes <= smem_budget) { mode = MkpermMode::Cta; warps = 32; }
     else { mode = MkpermMode::Global; warps = 32; }
 
-    // Developer override for A/B measurements: DRJIT_B200_MKPERM_MODE=warp|cta|global
+#if defined(DRJIT_B200_EXPERIMENTS)
+    // A/B measurements: DRJIT_B200_MKPERM_MODE=warp|cta|global
     if (const char *env = getenv("DRJIT_B200_MKPERM_MODE")) {
         if (!strcmp(env, "cta") && bytes <= smem_budget) { mode = MkpermMode::Cta; warps = 32; }
         else if (!strcmp(env, "global")) { mode = MkpermMode::Global; warps = 32; }
         else if (!strcmp(env, "warp") && w >= 1) { mode = MkpermMode::Warp; warps = w; }
     }
+#endif
     return mode;
 }
 
 template <MkpermMode Mode>
 static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads, uint32_t smem,
                           uint32_t *offsets_dev, uint32_t *unique_dev, uint32_t *hist_out,
-                          cudaEvent_t table_ready) {
+                          cudaEvent_t table_ready, const MkpermPeer *peer) {
     const uint32_t grid = p.ctas_per_group * p.n_groups;
     if (smem > 48 * 1024) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_histogram_kernel<Mode>,
@@ -994,8 +1044,7 @@ static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads
         mkperm_column_scan_kernel<<<tiles * p.n_groups, 256, 0, stream>>>(p, tiles);
         DJB_POST_LAUNCH();
     }
-    mkperm_bucket_scan_kernel<<<p.n_groups, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out);
-    DJB_POST_LAUNCH();
+    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer);
     if (table_ready)
         DJB_CUDA_CHECK(cudaEventRecord(table_ready, stream)); // cuda_ts.cpp:953 (before phase 4)
     mkperm_scatter_kernel<Mode><<<grid, threads, smem, stream>>>(p);
@@ -1003,24 +1052,21 @@ static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads
 }
 
 
-static cudaEvent_t mkperm_event() {
-    static thread_local cudaEvent_t ev = nullptr;
-    static thread_local int ev_device = -1;
-    int device = device_props().device;
-    if (!ev || ev_device != device) {
-        DJB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        ev_device = device;
-    }
-    return ev;
-}
 
-/// Developer override for A/B measurements: DRJIT_B200_MKPERM_TILES=0 disables the tile path
+#if defined(DRJIT_B200_EXPERIMENTS)
+/// Integer environment variable, read once (experiments builds only)
+static int env_int(const char *name, int fallback) {
+    const char *env = getenv(name);
+    return env ? atoi(env) : fallback;
+}
+#endif
+
 static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_count) {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char *env = getenv("DRJIT_B200_MKPERM_TILES");
-        enabled = env ? atoi(env) != 0 : 1;
-    }
+#if defined(DRJIT_B200_EXPERIMENTS)
+    static const int enabled = env_int("DRJIT_B200_MKPERM_TILES", 1);  // =0 disables the tile path
+#else
+    constexpr int enabled = 1;
+#endif
     const uint64_t tiles = ceil_div64(size, 512 * kTileKeysPerThread);
     return enabled && n_groups == 1 && bucket_count <= kTileMaxBuckets && size >= (1u << 18) &&
            tiles * bucket_count * 6 <= ((uint64_t) 2 << 30);
@@ -1028,12 +1074,12 @@ static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_coun
 
 template <uint32_t THREADS, uint32_t KEY_BITS>
 static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t, uint32_t grid, uint32_t smem, uint32_t smem_max) {
-    static bool configured_on[kMaxDevices] = {};       // (function attributes are per device)
-    bool &configured = configured_on[device_props().device % kMaxDevices];
-    if (!configured) {
+    static std::atomic<bool> configured_on[kMaxDevices] = {};       // (function attributes are per device)
+    std::atomic<bool> &configured = configured_on[device_props().device % kMaxDevices];
+    if (!configured.load(std::memory_order_acquire)) {     // (idempotent: a race only repeats the call)
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_max));
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS><<<grid, THREADS, smem, stream>>>(t);
 }
@@ -1041,7 +1087,7 @@ static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t
 template <uint32_t THREADS, bool STABLE, uint32_t KPT = kTileKeysPerThread>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
-                             uint32_t *offsets, uint32_t *hist_out) {
+                             uint32_t *offsets, uint32_t *hist_out, const MkpermPeer *peer) {
     static_assert(!STABLE || KPT == kTileKeysPerThread, "the stable kernel has 32 keys per thread");
     constexpr uint32_t TILE = THREADS * KPT;
     const DeviceProps &dev = device_props();
@@ -1051,16 +1097,18 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     t.index_base = index_base;
     t.tiles = (uint32_t) ceil_div64(size, TILE);
     t.vec = ((uintptr_t) values % 16) == 0;
+#if defined(DRJIT_B200_EXPERIMENTS)
     {
-        static int debug = -1;
-        if (debug < 0) {
-            const char *env = getenv("DRJIT_B200_MKPERM_DEBUG");
-            debug = env ? atoi(env) : 0;
-        }
+        static const int debug = env_int("DRJIT_B200_MKPERM_DEBUG", 0);
         t.debug = (uint8_t) debug;
     }
+#endif
 
+#if defined(DRJIT_B200_EXPERIMENTS)
     constexpr bool STAGE16 = !STABLE && KPT >= 60;       // 16-bit staging entries (mkperm_tile_scatter16_kernel)
+#else
+    constexpr bool STAGE16 = false;
+#endif
     const uint32_t hist_smem = t.stride * 8,
                    scatter_smem = STABLE ? (THREADS / 32 + 1) * t.stride * 4 + TILE * 4
                                 : STAGE16 ? t.stride * 10 + TILE / 32 * 6 + TILE * 2
@@ -1101,18 +1149,21 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
         DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &unique_dev, pinned + 1, 0));
     }
 
-    static bool configured_on[kMaxDevices] = {};       // (function attributes are per device)
-    bool &configured = configured_on[dev.device % kMaxDevices];
-    if (!configured) {
+    static std::atomic<bool> configured_on[kMaxDevices] = {};       // (function attributes are per device)
+    std::atomic<bool> &configured = configured_on[dev.device % kMaxDevices];
+    if (!configured.load(std::memory_order_acquire)) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_hist_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int) (kTileMaxBuckets * 8)));
+#if defined(DRJIT_B200_EXPERIMENTS)
         if constexpr (STAGE16)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter16_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int) (dev.smem_optin - 1024)));
-        else if (!STABLE)
+        else
+#endif
+        if (!STABLE)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4, dev.smem_optin - 1024)));
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     if (!STABLE && scatter_smem > dev.smem_optin - 1024)
         raise(DRJIT_B200_EFATAL, "jit_block_mkperm(): internal error (tile does not fit into shared memory)");
@@ -1122,9 +1173,8 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     const uint32_t col_tiles = ceil_div(bucket_count, 32);
     mkperm_column_scan_kernel<<<col_tiles, 256, 0, stream>>>(p, col_tiles);
     DJB_POST_LAUNCH();
-    mkperm_bucket_scan_kernel<<<1, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out);
-    DJB_POST_LAUNCH();
-    cudaEvent_t ev = want_table ? mkperm_event() : nullptr;
+    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer);
+    cudaEvent_t ev = want_table ? thread_event() : nullptr;
     if (ev)
         DJB_CUDA_CHECK(cudaEventRecord(ev, stream));       // cuda_ts.cpp:953 (before the scatter pass)
     if (STABLE) {
@@ -1137,16 +1187,40 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     } else {
         const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
         const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
+#if defined(DRJIT_B200_EXPERIMENTS)
         if constexpr (STAGE16)
             mkperm_tile_scatter16_kernel<THREADS, KPT><<<std::min(t.tiles, dev.sm_count), THREADS, scatter_smem, stream>>>(t);
         else
+#endif
             mkperm_tile_scatter_kernel<THREADS, KPT><<<grid, THREADS, scatter_smem, stream>>>(t);
     }
     DJB_POST_LAUNCH();
 
     if (!want_table)
         return 0;
+    scratch.unlock();                                      // (never block on the GPU with the stream's lock held)
     DJB_CUDA_CHECK(cudaEventSynchronize(ev));              // cuda_ts.cpp:964-967
+    return pinned[1];
+}
+
+/// An empty trailing shard of a sharded call still takes part in the histogram exchange
+static uint32_t mkperm_empty_shard(cudaStream_t stream, uint32_t bucket_count, uint32_t *offsets,
+                                   uint32_t *hist_out, const MkpermPeer *peer) {
+    MkpermParams p{};
+    p.bucket_count = bucket_count; p.n_groups = 1;
+    Scratch scratch(stream);
+    p.totals = (uint32_t *) scratch.device((size_t) bucket_count * 4);
+    DJB_CUDA_CHECK(cudaMemsetAsync(p.totals, 0, (size_t) bucket_count * 4, stream));
+    uint32_t *offsets_dev = nullptr, *unique_dev = nullptr, *pinned = scratch.pinned_words();
+    if (offsets) {
+        DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &offsets_dev, offsets, 0));
+        DJB_CUDA_CHECK(cudaHostGetDevicePointer((void **) &unique_dev, pinned + 1, 0));
+    }
+    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer);
+    if (!offsets)
+        return 0;
+    scratch.unlock();
+    DJB_CUDA_CHECK(cudaStreamSynchronize(stream));
     return pinned[1];
 }
 
@@ -1155,11 +1229,14 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
 /// `offsets` is given and there is a single group (after waiting for the table), else 0.
 static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_t size,
                             uint32_t block_size, uint32_t bucket_count, uint32_t index_base,
-                            uint32_t *perm, uint32_t *offsets, uint32_t *hist_out) {
-    if (size == 0)
-        return 0;
+                            uint32_t *perm, uint32_t *offsets, uint32_t *hist_out,
+                            const MkpermPeer *peer = nullptr) {
     if (bucket_count == 0) // cuda_ts.cpp:794-795 (jitc_fail)
         raise(DRJIT_B200_EFATAL, "jit_block_mkperm(): bucket_count cannot be zero!");
+    if (size == 0 && peer)
+        return mkperm_empty_shard(stream, bucket_count, offsets, hist_out, peer);
+    if (size == 0)
+        return 0;
     if (block_size == 0 || block_size > size)
         raise(DRJIT_B200_EINVAL, "jit_block_mkperm(): invalid block size (size=%u, block_size=%u)!",
               size, block_size);
@@ -1175,45 +1252,47 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
         // Where the reference's "tiny" variant applies (bucket_count * 4 B * 32 warps fit into shared
         // memory, jit.h:2404-2406, cuda_ts.cpp:824-836) its permutation is stable and dr.sort depends
         // on that, so is ours; beyond it the reference is unordered as well and the faster unordered
-        // tile kernel is used. DRJIT_B200_MKPERM_UNORDERED=1 forces the latter (A/B measurements only).
-        static int force_unordered = -1;
-        if (force_unordered < 0) {
-            const char *env = getenv("DRJIT_B200_MKPERM_UNORDERED");
-            force_unordered = env ? atoi(env) != 0 : 0;
-        }
+        // tile kernel is used.
+#if defined(DRJIT_B200_EXPERIMENTS)
+        static const int force_unordered = env_int("DRJIT_B200_MKPERM_UNORDERED", 0);  // A/B measurements
+#else
+        constexpr int force_unordered = 0;
+#endif
         const bool stable = (uint64_t) bucket_count * 4 * 32 <= dev.smem_optin && !force_unordered;
         // 32 per-warp counter rows + a 32 Ki-key tile fit up to 512 buckets; inputs that would leave
         // a quarter of the SMs without such a tile take 16 Ki-key tiles (twice as many CTAs at work:
         // 2^18..2^21 keys 45 -> 35 us, scripts/small_sizes.py)
         if (stable && bucket_count <= 512 && size >= dev.sm_count * 24576u)
-            return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+            return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
         if (stable)                             // 16 rows + a 16 Ki-key tile (up to 1816 buckets)
-            return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+            return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
         // Unordered kernel: what bounds its scatter pass is the length of a bucket's run per tile
         // (profiles/r1b_microbench.txt), so the tile is as large as shared memory allows: 48 Ki keys
         // (two 16-bit keys per register) next to the two bucket rows up to 4352 buckets, 32 Ki keys
-        // then 40 Ki keys up to 8192. DRJIT_B200_MKPERM_KPT=32|40|48 caps the tile (A/B measurements only).
-        static int kpt_env = -1;
-        if (kpt_env < 0) {
-            const char *env = getenv("DRJIT_B200_MKPERM_KPT");
-            kpt_env = env ? atoi(env) : 0;
-        }
+        // then 40 Ki keys up to 8192.
+#if defined(DRJIT_B200_EXPERIMENTS)
+        static const int kpt_env = env_int("DRJIT_B200_MKPERM_KPT", 0);   // 32|40|48|60 caps the tile (A/B measurements)
+#else
+        constexpr int kpt_env = 0;
+#endif
         const uint32_t stride = (bucket_count + 7) / 8 * 8;
         auto fits = [&](uint32_t kpt) {
             return stride * 8 + 1024 * kpt * 4 <= dev.smem_optin - 1024 && size >= dev.sm_count * 2u * 1024u * kpt;
         };
         const uint32_t kpt = kpt_env ? (uint32_t) kpt_env : kMkpermDefaultKpt;
+#if defined(DRJIT_B200_EXPERIMENTS)
         // (experimental, only by request: 60 Ki-key tiles with 16-bit staging entries)
         if (kpt_env == 60 && stride * 10 + 1024 * 60 / 32 * 6 + 1024 * 60 * 2 <= dev.smem_optin - 1024 &&
             size >= dev.sm_count * 2u * 1024u * 60u)
-            return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+            return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+#endif
         // (two co-resident 512-thread CTAs with 20 Ki / 16 Ki-key tiles were measured and are slower:
         // 0.396 / 0.499 ms against 0.348 ms, profiles/r2o_mkperm_tile_keys.txt)
         if (kpt >= 48 && fits(48))
-            return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+            return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
         if (kpt >= 40 && fits(40))
-            return mkperm_tiles<1024, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
-        return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out);
+            return mkperm_tiles<1024, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+        return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
     }
 
     uint32_t warps = 32;
@@ -1268,21 +1347,22 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
 
     const uint32_t smem = mode == MkpermMode::Warp ? warps * bucket_count * 4
                         : mode == MkpermMode::Cta ? bucket_count * 4 : 0;
-    cudaEvent_t ev = want_table ? mkperm_event() : nullptr;
+    cudaEvent_t ev = want_table ? thread_event() : nullptr;
     switch (mode) {
         case MkpermMode::Warp:
-            launch_phases<MkpermMode::Warp>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev);
+            launch_phases<MkpermMode::Warp>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer);
             break;
         case MkpermMode::Cta:
-            launch_phases<MkpermMode::Cta>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev);
+            launch_phases<MkpermMode::Cta>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer);
             break;
         default:
-            launch_phases<MkpermMode::Global>(stream, p, threads, 0, offsets_dev, unique_dev, hist_out, ev);
+            launch_phases<MkpermMode::Global>(stream, p, threads, 0, offsets_dev, unique_dev, hist_out, ev, peer);
             break;
     }
 
     if (!want_table)
         return 0;
+    scratch.unlock();
     DJB_CUDA_CHECK(cudaEventSynchronize(ev)); // cuda_ts.cpp:964-967: table valid, perm still in flight
     return pinned[1];
 }
@@ -1300,6 +1380,23 @@ void mkperm_sharded(cudaStream_t stream, const uint32_t *values, uint32_t size, 
         return;
     }
     mkperm_impl(stream, values, size, size, bucket_count, index_base, perm, nullptr, hist_dev);
+}
+
+/// Shard-local permutation of one sorting group that is sharded over the ranks of a communicator,
+/// fused with the exchange of the shard histograms (inside the bucket-scan kernel, no library
+/// collective, no host round trip): perm = this shard's permutation with entries index_base + local
+/// index; hist_dev[b] = this shard's count of bucket b; rank_base_dev[b] = where this rank's keys of
+/// bucket b start in the global rank-major (= stable) order; offsets (pinned host, may be NULL) = the
+/// table of non-empty buckets of the GLOBAL array, identical on every rank. Returns the unique count
+/// when `offsets` is given (after waiting for the table, like the single-GPU call).
+uint32_t comm_mkperm(cudaStream_t stream, const Comm *comm, const uint32_t *values, uint32_t size,
+                     uint32_t bucket_count, uint32_t index_base, uint32_t *perm, uint32_t *hist_dev,
+                     uint32_t *rank_base_dev, uint32_t *offsets) {
+    MkpermPeer peer{ comm_ctx(comm), rank_base_dev };
+    if ((uint64_t) bucket_count * 4 > kSlotBytes)
+        raise(DRJIT_B200_EINVAL, "drjit_b200_comm_mkperm(): at most %u buckets fit the exchange window (got %u)!",
+              kSlotBytes / 4, bucket_count);
+    return mkperm_impl(stream, values, size, std::max(size, 1u), bucket_count, index_base, perm, offsets, hist_dev, &peer);
 }
 
 } // namespace djb

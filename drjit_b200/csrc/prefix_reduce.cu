@@ -11,6 +11,7 @@
 #include "scan_kernel.cuh"
 #include "runtime.h"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace djb {
@@ -33,14 +34,15 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     constexpr uint32_t threads = ScanRoles<SEG, STAGES>::THREADS;
 
     // (function attributes and occupancy are per device: one slot per device and instantiation)
-    static int occupancy_of[kMaxDevices] = {};
-    int &occupancy = occupancy_of[dev.device % kMaxDevices];
-    if (occupancy == 0) {
+    static std::atomic<int> occupancy_of[kMaxDevices] = {};
+    int occupancy = occupancy_of[dev.device % kMaxDevices].load(std::memory_order_acquire);
+    if (occupancy == 0) {                                   // (idempotent: a race only repeats the queries)
         // (static + dynamic shared memory together may exceed the 48 KiB default)
         if (smem >= 32 * 1024)
             DJB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         DJB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, kernel, threads, smem));
         if (occupancy < 1) occupancy = 1;
+        occupancy_of[dev.device % kMaxDevices].store(occupancy, std::memory_order_release);
     }
 
     p.tiles = ceil_div(p.size, Geom::TILE);
@@ -182,28 +184,6 @@ template <typename T> static void prefix_ops_float(cudaStream_t s, int vt, int o
     }
 }
 
-/// Reduction identity as raw bits (jitc_reduce_identity, src/var.cpp:2642-2652)
-static uint64_t reduce_identity(int vt, int op) {
-    const uint32_t ts = type_size(vt);
-    const bool sgn = vt == DRJIT_B200_VT_INT8 || vt == DRJIT_B200_VT_INT16 ||
-                     vt == DRJIT_B200_VT_INT32 || vt == DRJIT_B200_VT_INT64;
-    const bool flt = vt == DRJIT_B200_VT_FLOAT16 || vt == DRJIT_B200_VT_FLOAT32 || vt == DRJIT_B200_VT_FLOAT64;
-    const uint64_t ones = ts == 8 ? ~0ull : ((1ull << (8 * ts)) - 1);
-    switch (op) {
-        case DRJIT_B200_OP_AND: return ones;
-        case DRJIT_B200_OP_MUL:
-            if (!flt) return 1;
-            return vt == DRJIT_B200_VT_FLOAT16 ? 0x3C00ull : vt == DRJIT_B200_VT_FLOAT32 ? 0x3F800000ull : 0x3FF0000000000000ull;
-        case DRJIT_B200_OP_MIN:
-            if (flt) return vt == DRJIT_B200_VT_FLOAT16 ? 0x7C00ull : vt == DRJIT_B200_VT_FLOAT32 ? 0x7F800000ull : 0x7FF0000000000000ull;
-            return sgn ? ones >> 1 : ones;
-        case DRJIT_B200_OP_MAX:
-            if (flt) return vt == DRJIT_B200_VT_FLOAT16 ? 0xFC00ull : vt == DRJIT_B200_VT_FLOAT32 ? 0xFF800000ull : 0xFFF0000000000000ull;
-            return sgn ? (ones >> 1) + 1 : 0;
-        default: return 0; // Add, Or
-    }
-}
-
 void block_prefix_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uint32_t block_size,
                          bool exclusive, bool reverse, const void *in, void *out,
                          const void *carry_in, void *total_out) {
@@ -262,6 +242,45 @@ void block_prefix_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uin
             raise(DRJIT_B200_EUNSUPPORTED, "jit_block_prefix_reduce(): no existing kernel for type=%s, op=%s!",
                   type_name(vt), op_name(op));
     }
+}
+
+/// Prefix reduction of a global array cut into contiguous per-rank shards.
+///  materialise: every element carries the global value. Rank r cannot emit its first output before
+///      all lower ranks have read their whole shard, so the minimum for contiguous shards is one
+///      extra read pass: launch 1 reduces the shard and exchanges the totals through peer memory
+///      inside its last CTA (fold over the lower ranks = this shard's carry), launch 2 is the
+///      single-pass scan seeded with that carry. 12 B/element for 4-byte types, no library collective.
+///  !materialise ("shard-offset form"): the local scan (8 B/element; its total falls out of the
+///      kernel) followed by a one-thread exchange kernel; `out` holds the shard-local prefix and
+///      *offset_out the fold over the lower ranks, global[i] = op(offset, local[i]).
+/// offset_out (device scalar of type vt, may be NULL when materialising) receives the carry.
+void comm_prefix_reduce(cudaStream_t stream, const Comm *comm, int vt, int op, uint32_t size, bool exclusive,
+                        bool reverse, const void *in, void *out, void *offset_out, bool materialise) {
+    const uint32_t tsize = type_size(vt);
+    if (tsize == 0 || op < DRJIT_B200_OP_ADD || op > DRJIT_B200_OP_OR)
+        raise(DRJIT_B200_EUNSUPPORTED, "jit_block_prefix_reduce(): no existing kernel for type=%s, op=%s!",
+              type_name(vt), op_name(op));
+    const uint32_t fold = reverse ? 2u /* ranks above */ : 1u /* ranks below */;
+    Scratch scratch(stream);                 // (kept across the inner calls: they nest)
+    void *carry = offset_out ? offset_out : scratch.device(256);
+    if (materialise) {
+        comm_reduce(stream, comm, vt, op, fold, size, in, carry);
+        if (size)
+            block_prefix_reduce(stream, vt, op, size, size, exclusive, reverse, in, out, carry, nullptr);
+        return;
+    }
+    if (!offset_out)
+        raise(DRJIT_B200_EINVAL, "drjit_b200_comm_prefix_reduce(): the shard-offset form needs offset_out!");
+    // u8 / f16 totals travel as 4-byte accumulators in the fused reduction; the scalar exchange
+    // kernel handles the 4- and 8-byte types the scan totals of this form come in.
+    void *total = scratch.device(256);
+    if (size) {
+        block_prefix_reduce(stream, vt, op, size, size, exclusive, reverse, in, out, nullptr, total);
+    } else {
+        const uint64_t ident = reduce_identity(vt, op);
+        memset_async(stream, total, 1, tsize, &ident);
+    }
+    comm_fold_scalar(stream, comm, vt, op, fold, total, offset_out);
 }
 
 } // namespace djb

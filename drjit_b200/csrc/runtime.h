@@ -50,13 +50,24 @@ struct DeviceProps {
 const DeviceProps &device_props();
 
 /// Scratch memory for one primitive call. Obtained from the user allocator hooks when
-/// installed (jitc_malloc-style, released when the object dies), otherwise from a
-/// grow-only arena owned by the library and keyed by (device, stream): successive
-/// kernels on one stream are ordered, so the arena can be reused without a sync.
+/// installed (jitc_malloc-style, released when the object dies -- the hook's free must be
+/// stream-ordered like jitc_free(), see drjit_b200.h), otherwise from a grow-only arena owned
+/// by the library and keyed by (device, stream): successive kernels on one stream are ordered,
+/// so the arena can be reused without a sync. The arena never shrinks and is never freed while
+/// work may still use it: a grown arena's predecessor is retired behind an event. While the
+/// stream is being captured into a CUDA graph the arena cannot grow (cudaMalloc is not
+/// capturable): reserve it beforehand with drjit_b200_reserve_scratch() or one warm-up call.
+///
+/// The object holds the stream's mutex from construction until unlock() / destruction, i.e.
+/// while kernels are being *enqueued*; it must be unlock()ed before the host blocks on the GPU.
 class Scratch {
 public:
     Scratch(cudaStream_t stream);
     ~Scratch();
+    /// Release the stream's mutex early (before cudaStreamSynchronize / cudaEventSynchronize).
+    /// No device() / reserve() calls afterwards; pointers handed out stay valid for the kernels
+    /// already enqueued, and pinned_slot() stays private to this call.
+    void unlock();
     Scratch(const Scratch &) = delete;
     Scratch &operator=(const Scratch &) = delete;
 
@@ -70,21 +81,46 @@ public:
     /// primitive; kernels that use it must leave it zeroed (self-cleaning counters).
     uint32_t *zeroed_counters();
     static constexpr size_t kZeroedCounters = 4096; // number of u32 counters
-    /// Pinned, device-mapped host words private to this stream (results read by the host)
+    /// kPinnedSlotWords pinned, device-mapped host words (results read by the host after a wait).
+    /// Slots rotate per call (kPinnedSlots of them per stream), so a call that has unlock()ed can
+    /// still read its own slot after the wait while another thread enqueues on the same stream.
     uint32_t *pinned_words();
-    static constexpr size_t kPinnedWords = 64;
+    static constexpr size_t kPinnedSlots = 32, kPinnedSlotWords = 16, kPinnedWords = kPinnedSlotWords * kPinnedSlots;
 
     struct StreamState;
 
 private:
     StreamState *m_state;
     cudaStream_t m_stream;
-    size_t m_used = 0;
+    size_t m_base = 0;          // arena bytes in use by enclosing Scratch objects
     void *m_user_allocs[8];
     int m_user_alloc_count = 0;
+    bool m_locked = true;
+    uint32_t *m_pinned = nullptr;
+    // allocator hooks, snapshotted under the library lock at construction
+    drjit_b200_malloc_fn m_malloc_fn = nullptr;
+    drjit_b200_free_fn m_free_fn = nullptr;
+    void *m_alloc_user = nullptr;
 };
 
+/// Event (timing disabled) private to the calling thread and the current device
+cudaEvent_t thread_event();
+
 void count_launch();
+
+/// Brackets one primitive call at the C-ABI boundary: launch hook (KernelHistory / LaunchBlocking,
+/// src/cuda_ts.cpp:19-46) before the first and after the last launch of the call.
+class CallScope {
+public:
+    CallScope(int kernel_type, uint32_t size, cudaStream_t stream);
+    ~CallScope();
+private:
+    int m_type; uint32_t m_size; cudaStream_t m_stream;
+    uint64_t m_launches_before;
+    void *m_cookie = nullptr;
+    cudaEvent_t m_start = nullptr;
+    bool m_history = false, m_blocking = false, m_hooked = false;
+};
 
 /// Launch-error check + accounting after every kernel launch (submit_gpu, cuda_ts.cpp:12-47)
 #define DJB_POST_LAUNCH()                                                                \
@@ -97,6 +133,8 @@ inline uint32_t round_pow2(uint32_t x) { uint32_t r = 1; while (r < x) r <<= 1; 
 const char *type_name(int vt);
 const char *op_name(int op);
 uint32_t type_size(int vt);
+/// Reduction identity as raw bits (jitc_reduce_identity, src/var.cpp:2642-2652)
+uint64_t reduce_identity(int vt, int op);
 
 // ---- primitive implementations (one translation unit each) ------------------------
 void memset_async(cudaStream_t s, void *ptr, uint32_t size, uint32_t isize, const void *src);
@@ -120,5 +158,29 @@ void scatter_reduce(cudaStream_t s, int vt, int op, int mode, void *target, uint
                     const void *value, const uint32_t *index, const uint8_t *mask, uint32_t size);
 void fill_fmix32(cudaStream_t s, int kind, void *out, uint64_t start, uint64_t n, uint32_t xor_,
                  uint32_t and_);
+
+// ---- multi-GPU forms: the primitive fused with its combine over the ranks of a peer-memory
+//      communicator (comm.cu / comm.cuh) ------------------------------------
+struct Comm;
+Comm *comm_create(uint32_t rank, uint32_t world, size_t bulk_bytes);
+void comm_handle(const Comm *c, void *handle_out);
+void comm_connect_ipc(Comm *c, const void *handles);
+void comm_connect_local(Comm **comms, uint32_t world);
+void comm_destroy(Comm *c);
+uint32_t comm_rank(const Comm *c);
+uint32_t comm_world(const Comm *c);
+void comm_fold_scalar(cudaStream_t s, const Comm *c, int vt, int op, uint32_t fold, const void *src, void *dst);
+void comm_allgather(cudaStream_t s, const Comm *c, const void *src, uint32_t bytes, void *dst);
+void comm_allreduce(cudaStream_t s, const Comm *c, int vt, int op, void *data, uint32_t n);
+void comm_reduce(cudaStream_t s, const Comm *c, int vt, int op, uint32_t fold, uint32_t size, const void *in, void *out);
+void comm_reduce_dot(cudaStream_t s, const Comm *c, int vt, const void *a, const void *b, uint32_t size, void *out);
+bool comm_all_any(cudaStream_t s, const Comm *c, const uint8_t *values, uint32_t size, int op);
+void comm_prefix_reduce(cudaStream_t s, const Comm *c, int vt, int op, uint32_t size, bool exclusive, bool reverse,
+                        const void *in, void *out, void *offset_out, bool materialise);
+void comm_compress(cudaStream_t s, const Comm *c, const uint8_t *in, uint32_t size, uint32_t index_base,
+                   uint32_t *out, uint32_t *counts_host);
+uint32_t comm_mkperm(cudaStream_t s, const Comm *c, const uint32_t *values, uint32_t size, uint32_t bucket_count,
+                     uint32_t index_base, uint32_t *perm, uint32_t *hist_dev, uint32_t *rank_base_dev,
+                     uint32_t *offsets);
 
 } // namespace djb

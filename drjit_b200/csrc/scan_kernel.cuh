@@ -115,7 +115,7 @@ struct PrefixParams {
     uint64_t magic;         // floor(2^64 / block_size) (+ 1 unless block_size is a power of two)
     uint32_t size, block_size, tiles;
     uint8_t exclusive, reverse, in_place;
-    uint8_t debug;          // timing experiments only (scripts/sweep_scan.cu): 1 = skip look-back, 2 = skip stores
+    uint8_t debug;          // read only in -DDRJIT_B200_EXPERIMENTS builds (scripts/sweep_scan.cu): 1 = skip look-back, 2 = skip stores
 };
 
 /// Tile geometry. A "unit" is what one thread moves at once (a 128-bit vector, or one element
@@ -340,7 +340,7 @@ prefix_reduce_kernel(const PrefixParams p) {
                 }
             }
         }
-        const uint32_t win_n = (p.debug & 1) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
+        const uint32_t win_n = (DJB_DEBUG(p.debug) & 1) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
         if constexpr (WINDOW) {
             #pragma unroll
             for (uint32_t j = 0; j < kScanWindowLoads; ++j) {
@@ -525,7 +525,7 @@ prefix_reduce_kernel(const PrefixParams p) {
                     if (p.carry_in) excl = to_acc<A>(*(const T *) p.carry_in);
                     if (lane == 0)
                         state.publish(0, kPrefix, tf ? tv : Op::template apply<A>(excl, tv));
-                } else if (p.debug & 1) {
+                } else if (DJB_DEBUG(p.debug) & 1) {
                     excl = ident;
                 } else {
                     if (lane == 0 && tf)
@@ -573,7 +573,7 @@ prefix_reduce_kernel(const PrefixParams p) {
                 #pragma unroll
                 for (uint32_t e = 0; e < V; ++e)
                     v.v[rev ? V - 1 - e : e] = from_acc<T>(res[e]);
-                if ((p.debug & 2) && v.v[0] != T(12345))
+                if ((DJB_DEBUG(p.debug) & 2) && v.v[0] != T(12345))
                     continue;
                 st_stream<T>(rev ? out + (size - s0 - V) : out + s0, v);
             } else {

@@ -45,15 +45,18 @@ DJB_ATOMIC(OpAnd, uint32_t, atomicAnd(addr, v))
 DJB_ATOMIC(OpAnd, uint64_t, atomicAnd((unsigned long long *) addr, (unsigned long long) v))
 DJB_ATOMIC(OpOr, uint32_t, atomicOr(addr, v))
 DJB_ATOMIC(OpOr, uint64_t, atomicOr((unsigned long long *) addr, (unsigned long long) v))
-// float min/max: non-negative values order like signed ints, negative ones like reversed
-// unsigned ints (cuda_scatter.cpp:74-106)
-DJB_ATOMIC(OpMin, float, if (!(v < 0.f)) atomicMin((int *) addr, __float_as_int(v));
+// float min/max: values with a clear sign bit order like signed ints, values with the sign bit set
+// like reversed unsigned ints. The branch tests the BIT PATTERN like the reference's
+// `setp.ge.s32` (cuda_scatter.cpp:98-105), not the float value: -0.0 (0x80000000) must take the
+// unsigned path -- as a signed int it is INT_MIN, which atomicMin would store over any more
+// negative target and atomicMax would never store.
+DJB_ATOMIC(OpMin, float, if (__float_as_int(v) >= 0) atomicMin((int *) addr, __float_as_int(v));
                          else atomicMax((unsigned *) addr, __float_as_uint(v)))
-DJB_ATOMIC(OpMax, float, if (!(v < 0.f)) atomicMax((int *) addr, __float_as_int(v));
+DJB_ATOMIC(OpMax, float, if (__float_as_int(v) >= 0) atomicMax((int *) addr, __float_as_int(v));
                          else atomicMin((unsigned *) addr, __float_as_uint(v)))
-DJB_ATOMIC(OpMin, double, if (!(v < 0.0)) atomicMin((long long *) addr, __double_as_longlong(v));
+DJB_ATOMIC(OpMin, double, if (__double_as_longlong(v) >= 0) atomicMin((long long *) addr, __double_as_longlong(v));
                           else atomicMax((unsigned long long *) addr, (unsigned long long) __double_as_longlong(v)))
-DJB_ATOMIC(OpMax, double, if (!(v < 0.0)) atomicMax((long long *) addr, __double_as_longlong(v));
+DJB_ATOMIC(OpMax, double, if (__double_as_longlong(v) >= 0) atomicMax((long long *) addr, __double_as_longlong(v));
                           else atomicMin((unsigned long long *) addr, (unsigned long long) __double_as_longlong(v)))
 #undef DJB_ATOMIC
 

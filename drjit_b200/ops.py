@@ -53,6 +53,51 @@ def launch_count(reset=False):
     return int(lib.drjit_b200_launch_count(int(reset)))
 
 
+class KernelType(enum.IntEnum):  # include/drjit-core/jit.h:2597-2632 (+ this library's extensions >= 256)
+    JIT = 0; BlockReduce = 1; BlockPrefixReduce = 2; Dot = 3; BatchedGemm = 4; Compress = 5
+    MkPerm = 6; Memcpy = 7; Memset = 8; Poke = 9; Aggregate = 10; LLVMHostFunc = 11
+    ScatterReduce = 256; Sort = 257; PeerExchange = 258
+
+
+class JitFlag(enum.IntFlag):     # the two flags of jit.h:1680-1783 that act at the seam (cuda_ts.cpp:19-46)
+    KernelHistory = 1; LaunchBlocking = 2
+
+
+class _HistoryEntry(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_uint32), ("size", ctypes.c_uint32), ("launches", ctypes.c_uint32),
+                ("execution_time", ctypes.c_float)]
+
+
+def set_flag(flag, value=True):
+    """dr.set_flag(dr.JitFlag.KernelHistory, True) -- thread-local, like the reference."""
+    cur = int(lib.drjit_b200_flags())
+    lib.drjit_b200_set_flags(cur | int(flag) if value else cur & ~int(flag))
+
+
+def flag(flag):   # noqa: A002
+    return bool(int(lib.drjit_b200_flags()) & int(flag))
+
+
+def kernel_history(max_entries=4096):
+    """dr.kernel_history(): list of dicts {backend, type, size, launches, execution_time (ms)} for the
+    primitive calls recorded since the last call (src/python/history.cpp); clears the history."""
+    buf = (_HistoryEntry * max_entries)()
+    n = int(lib.drjit_b200_kernel_history(ctypes.cast(buf, ctypes.c_void_p), max_entries))
+    return [{"backend": "cuda", "type": KernelType(buf[i].type), "size": int(buf[i].size),
+             "launches": int(buf[i].launches), "execution_time": float(buf[i].execution_time)} for i in range(n)]
+
+
+def kernel_history_clear():
+    lib.drjit_b200_kernel_history_clear()
+
+
+def reserve_scratch(nbytes, device=None):
+    """Pre-size the library's scratch arena of the current stream (needed before CUDA-graph capture)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        check(lib.drjit_b200_reserve_scratch(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), int(nbytes)))
+
+
 def _vt(x, vt=None):
     if vt is not None:
         return VarType(vt)

@@ -60,6 +60,23 @@ enum drjit_b200_reduce_mode {       /* jit.h:1017-1066 */
     DRJIT_B200_MODE_PERMUTE = 5
 };
 
+/* KernelType, include/drjit-core/jit.h:2597-2632: the tag a launch carries in the kernel
+ * history. Values 0..11 are the reference's; >= 256 are primitives the reference has no
+ * precompiled kernel for (they run inside JIT kernels there). */
+enum drjit_b200_kernel_type {
+    DRJIT_B200_KT_JIT = 0, DRJIT_B200_KT_BLOCK_REDUCE = 1, DRJIT_B200_KT_BLOCK_PREFIX_REDUCE = 2,
+    DRJIT_B200_KT_DOT = 3, DRJIT_B200_KT_BATCHED_GEMM = 4, DRJIT_B200_KT_COMPRESS = 5,
+    DRJIT_B200_KT_MKPERM = 6, DRJIT_B200_KT_MEMCPY = 7, DRJIT_B200_KT_MEMSET = 8,
+    DRJIT_B200_KT_POKE = 9, DRJIT_B200_KT_AGGREGATE = 10, DRJIT_B200_KT_LLVM_HOST_FUNC = 11,
+    DRJIT_B200_KT_SCATTER_REDUCE = 256, DRJIT_B200_KT_SORT = 257, DRJIT_B200_KT_PEER_EXCHANGE = 258
+};
+
+/* Subset of JitFlag (jit.h:1680-1783) that acts at the seam (src/cuda_ts.cpp:19-46). */
+enum drjit_b200_flag {
+    DRJIT_B200_FLAG_KERNEL_HISTORY = 1,   /* JitFlag::KernelHistory: record an entry per primitive call */
+    DRJIT_B200_FLAG_LAUNCH_BLOCKING = 2   /* JitFlag::LaunchBlocking: synchronise the stream after each call */
+};
+
 enum drjit_b200_status {
     DRJIT_B200_OK = 0,
     DRJIT_B200_EINVAL = -1,        /* reference: jitc_raise() -> std::runtime_error */
@@ -91,7 +108,8 @@ DRJIT_B200_API const char *drjit_b200_version(void);
 DRJIT_B200_API int drjit_b200_init(void);
 
 /* Release scratch arenas and pinned staging buffers of all devices
- * (counterpart of jitc_cuda_shutdown(), src/cuda_core.cpp:541-582). */
+ * (counterpart of jitc_cuda_shutdown(), src/cuda_core.cpp:541-582). The caller must make sure
+ * that no other thread is inside the library and that all streams it was used on are idle. */
 DRJIT_B200_API int drjit_b200_shutdown(void);
 
 /* Scratch memory hooks. The reference obtains temporaries from its stream-ordered
@@ -104,9 +122,57 @@ typedef void (*drjit_b200_free_fn)(void *ptr, void *user);
 DRJIT_B200_API int drjit_b200_set_allocator(drjit_b200_malloc_fn malloc_fn,
                                             drjit_b200_free_fn free_fn, void *user);
 
+/* Scratch memory hooks, continued: `free_fn` MUST be stream-ordered like jitc_free()
+ * (src/malloc.cpp:202-260: the block is recycled only after the work enqueued before the free
+ * has finished): the library releases its temporaries as soon as the host call returns, while
+ * the kernels using them are still in flight on `stream`. Both hooks may be called from any
+ * thread that calls into the library. Install them before the first primitive call. */
+
+/* Make sure the library's own arena for `stream` (on the current device) holds at least `bytes`
+ * without a later cudaMalloc, e.g. before capturing calls into a CUDA graph: inside a capture the
+ * arena cannot grow and a primitive that needs more fails with DRJIT_B200_ECUDA. Capturable entry
+ * points are the asynchronous ones (everything except compress / all / any / block_mkperm with a
+ * host table, which block on the stream like their reference counterparts). A warm-up call of the
+ * same primitive at the same size has the same effect. No-op when allocator hooks are installed. */
+DRJIT_B200_API int drjit_b200_reserve_scratch(void *stream, size_t bytes);
+
 /* Number of kernels launched by this library on the calling thread since the last
  * call with reset != 0 (KernelHistory-style accounting, src/cuda_ts.cpp:19-46). */
 DRJIT_B200_API uint64_t drjit_b200_launch_count(int reset);
+
+/* ---- kernel history / launch blocking at the seam (src/cuda_ts.cpp:19-46) ----
+ * The reference's submit_gpu() brackets every primitive launch with two CUDA events and appends
+ * a KernelHistoryEntry{backend, type, size, ...} when JitFlag::KernelHistory is set, and
+ * synchronises after the launch when JitFlag::LaunchBlocking is set. Two ways to keep that
+ * working behind the seam:
+ *
+ * (a) Launch hook (what the drjit-core adapter installs, drjit_b200_thread_state.h): called on
+ *     the calling thread with phase 0 before the first launch of a primitive call and with
+ *     phase 1 after its last launch. `*cookie` is NULL at phase 0 and carries whatever the hook
+ *     stores there over to phase 1. `launches` (phase 1 only) is the number of kernels the call
+ *     enqueued -- 0 means the call was a no-op (size 0, plain memcpy ...) and nothing should be
+ *     recorded. A primitive is one entry (the reference records one per launch; full reductions
+ *     and scans are single launches here, mkperm is four). */
+typedef void (*drjit_b200_launch_hook)(void *user, int phase, int kernel_type, uint32_t size,
+                                       void *stream, uint32_t launches, void **cookie);
+DRJIT_B200_API int drjit_b200_set_launch_hook(drjit_b200_launch_hook hook, void *user);
+
+/* (b) Built-in history for use without Dr.Jit: flags are thread-local like JitFlag. */
+DRJIT_B200_API int drjit_b200_set_flags(uint32_t flags);
+DRJIT_B200_API uint32_t drjit_b200_flags(void);
+
+struct drjit_b200_history_entry {       /* the fields of KernelHistoryEntry this path fills in */
+    uint32_t type;                      /* enum drjit_b200_kernel_type */
+    uint32_t size;                      /* number of array entries processed */
+    uint32_t launches;                  /* kernels enqueued by the call */
+    float execution_time;               /* ms between the bracketing events */
+};
+/* Copies up to `max_entries` recorded entries of the calling thread (oldest first) into
+ * `entries`, waits for their events to obtain the timings, clears the history and returns the
+ * number copied (jit_kernel_history(), jit.h:2700-2710). */
+DRJIT_B200_API uint32_t drjit_b200_kernel_history(struct drjit_b200_history_entry *entries,
+                                                  uint32_t max_entries);
+DRJIT_B200_API void drjit_b200_kernel_history_clear(void);
 
 /* ---- the ThreadState seam (src/internal.h:902-962, src/cuda_ts.h:10-50) -- */
 
@@ -165,7 +231,9 @@ DRJIT_B200_API int drjit_b200_compress(void *stream, const uint8_t *in, uint32_t
  * apply (bucket_count * 4 bytes * 32 warps fit into shared memory: <= 1816 buckets on a B200), at
  * every input size; dr.sort / dr.argsort (LSD radix passes with 256 buckets) depend on it. Inputs
  * below 2^18 keys and block_size < size are stable up to 7264 buckets. Beyond that the keys of a
- * bucket appear in unspecified order, like in the reference's "small" / "large" variants. */
+ * bucket appear in unspecified order, like in the reference's "small" / "large" variants.
+ * Keys >= bucket_count are undefined behaviour in the reference; here every path counts and
+ * places them in the LAST bucket (no out-of-bounds access, same result at every input size). */
 DRJIT_B200_API int drjit_b200_block_mkperm(void *stream, const uint32_t *values, uint32_t size,
                                            uint32_t block_size, uint32_t bucket_count,
                                            uint32_t *perm, uint32_t *offsets,
@@ -222,6 +290,88 @@ DRJIT_B200_API int drjit_b200_compress_async(void *stream, const uint8_t *in, ui
 DRJIT_B200_API int drjit_b200_mkperm_sharded(void *stream, const uint32_t *values, uint32_t size,
                                              uint32_t bucket_count, uint32_t index_base,
                                              uint32_t *perm, uint32_t *hist_dev);
+
+/* ---- multi-GPU: primitives fused with their combine step over peer memory -------------------
+ * (new: the reference is single-device). One communicator per GPU of one
+ * NVSwitch box (<= DRJIT_B200_COMM_MAX_RANKS ranks). Each rank owns a "window" of device memory
+ * that all peers map (CUDA IPC between processes, plain peer access inside one process); the
+ * combine step of every primitive below is a few stores + flag spins over NVLink inside the
+ * kernel that produces the partial -- no library collective, no second launch, no host round
+ * trip. All ranks must issue the same sequence of comm calls, each rank on ONE stream; results
+ * that are defined for all ranks are bit-identical on all of them (fixed rank-order folds).
+ * A peer that never arrives makes the waiting kernel trap after ~20 s (loud failure, no hang). */
+#define DRJIT_B200_COMM_MAX_RANKS 8
+#define DRJIT_B200_COMM_HANDLE_BYTES 64
+#define DRJIT_B200_COMM_MAX_BUCKETS 16384      /* histogram exchange of drjit_b200_comm_mkperm */
+
+/* Creates this rank's communicator on the current device. bulk_bytes: capacity of the all-reduce
+ * staging area (>= padded byte size of the largest array passed to drjit_b200_comm_allreduce;
+ * 0 if unused). The window (1 MiB + 2 * bulk_bytes) is allocated and zeroed here. */
+DRJIT_B200_API int drjit_b200_comm_create(uint32_t rank, uint32_t world, size_t bulk_bytes, void **comm_out);
+/* One process per GPU: write this rank's DRJIT_B200_COMM_HANDLE_BYTES-byte window handle to
+ * handle_out, all-gather the handles by any means (the launcher's process group, MPI, a file), then connect
+ * with the `world` handles in rank order. */
+DRJIT_B200_API int drjit_b200_comm_handle(void *comm, void *handle_out);
+DRJIT_B200_API int drjit_b200_comm_connect(void *comm, const void *handles);
+/* All ranks inside one process (one thread or several; how Dr.Jit itself drives several devices,
+ * src/cuda_core.cpp:518-536): comms[r] = communicator of rank r. Enables peer access as needed. */
+DRJIT_B200_API int drjit_b200_comm_connect_local(void **comms, uint32_t world);
+/* Every rank must have finished its last comm call (and synchronised) before any rank destroys. */
+DRJIT_B200_API int drjit_b200_comm_destroy(void *comm);
+
+/* fold: which ranks' partials the result combines */
+enum drjit_b200_comm_fold {
+    DRJIT_B200_FOLD_ALL = 0,      /* all ranks: the reduction of the global array */
+    DRJIT_B200_FOLD_LOWER = 1,    /* ranks below the caller: carry of a forward scan */
+    DRJIT_B200_FOLD_HIGHER = 2    /* ranks above the caller: carry of a reverse scan */
+};
+
+/* jit_reduce / dr.sum|prod|min|max over a sharded array: reduction of this rank's shard
+ * in[0..size) and the fold over the ranks in ONE launch; out[0] (device) receives the result.
+ * size == 0 (empty trailing shard) contributes the identity. Same (vt, op) table as
+ * drjit_b200_block_reduce. */
+DRJIT_B200_API int drjit_b200_comm_reduce(void *comm, void *stream, int vt, int op, int fold, uint32_t size,
+                                          const void *in, void *out);
+/* jit_reduce_dot over sharded arrays, one launch. */
+DRJIT_B200_API int drjit_b200_comm_reduce_dot(void *comm, void *stream, int vt, const void *a, const void *b,
+                                              uint32_t size, void *out);
+/* dr.all / dr.any over a sharded mask (synchronous, like jitc_all / jitc_any). */
+DRJIT_B200_API int drjit_b200_comm_all(void *comm, void *stream, const uint8_t *values, uint32_t size, int *result);
+DRJIT_B200_API int drjit_b200_comm_any(void *comm, void *stream, const uint8_t *values, uint32_t size, int *result);
+/* Prefix reduction of a global array cut into contiguous shards in rank order.
+ * materialise != 0: out[i] is the global prefix value (two launches: shard reduction with the totals
+ *   exchanged inside its last CTA, then the single-pass scan seeded with the carry; 12 bytes per
+ *   4-byte element instead of 8 -- a rank cannot emit before all lower ranks have read their shard).
+ * materialise == 0: shard-offset form, out[i] = prefix inside the shard and *offset_out = fold over
+ *   the lower (reverse: higher) ranks, global[i] = op(offset, out[i]); 8 bytes per element.
+ * offset_out: device scalar of type vt (required for the offset form, optional otherwise). */
+DRJIT_B200_API int drjit_b200_comm_prefix_reduce(void *comm, void *stream, int vt, int op, uint32_t size,
+                                                 int exclusive, int reverse, const void *in, void *out,
+                                                 void *offset_out, int materialise);
+/* jit_compress of this rank's shard (indices are index_base + local index) and the exchange of the
+ * per-rank counts: counts_host[0..world) (host). Synchronous like the reference. */
+DRJIT_B200_API int drjit_b200_comm_compress(void *comm, void *stream, const uint8_t *in, uint32_t size,
+                                            uint32_t index_base, uint32_t *out, uint32_t *counts_host);
+/* jit_block_mkperm of one sorting group sharded over the ranks: perm (device, `size` entries) = this
+ * shard's permutation with entries index_base + local index; hist_dev[bucket_count] (device, may be
+ * NULL) = shard counts; rank_base_dev[bucket_count] (device, may be NULL) = start of this rank's keys
+ * of every bucket in the global rank-major (stable) order; offsets (host-pinned, 4*bucket_count+1,
+ * may be NULL) = table of non-empty buckets of the GLOBAL array {id, start, size, 0} + unique count,
+ * identical on every rank; the call waits for the table like drjit_b200_block_mkperm.
+ * bucket_count <= DRJIT_B200_COMM_MAX_BUCKETS. The histograms are exchanged inside the bucket-scan
+ * kernel. */
+DRJIT_B200_API int drjit_b200_comm_mkperm(void *comm, void *stream, const uint32_t *values, uint32_t size,
+                                          uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
+                                          uint32_t *hist_dev, uint32_t *rank_base_dev, uint32_t *offsets,
+                                          uint32_t *unique_out);
+/* In-place sum of `count` elements of data (device, 16-byte aligned; f32/f64/i32/u32/i64/u64) over all
+ * ranks -- the bins of a sharded dr.scatter_reduce(Add). One kernel: reduce-scatter + all-gather
+ * through the windows, every element folded once in rank order (bit-identical on all ranks). */
+DRJIT_B200_API int drjit_b200_comm_allreduce(void *comm, void *stream, int vt, int op, void *data, uint32_t count);
+/* Building blocks: all-gather of a small payload (bytes % 4 == 0, <= 64 KiB per rank; dst holds
+ * world * bytes, device or device-mapped host memory) and fold of one scalar per rank. */
+DRJIT_B200_API int drjit_b200_comm_allgather(void *comm, void *stream, const void *src, uint32_t bytes, void *dst);
+DRJIT_B200_API int drjit_b200_comm_fold(void *comm, void *stream, int vt, int op, int fold, const void *src, void *dst);
 
 /* Fill device arrays with the synthetic inputs of the benchmark (fmix32 of the element
  * index, ext/drjit-core/tests/reductions.cpp:5-13) without a host round trip.

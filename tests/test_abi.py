@@ -39,6 +39,20 @@ def test_library_exports_exactly_the_header():
         getattr(lib, name)
 
 
+def test_shipped_library_reads_no_environment():
+    """Developer switches (phase toggles, tile sizes, the experimental kernels) exist only in the
+    -DDRJIT_B200_EXPERIMENTS build that scripts/ use: the shipped library carries no DRJIT_B200_*
+    variable name and its sources call getenv() only inside experiments-only blocks."""
+    blob = open(LIB, "rb").read()
+    # (getenv itself is still imported: the statically linked CUDA runtime reads CUDA_* variables)
+    assert not re.search(rb"DRJIT_B200_[A-Z0-9_]+", blob), "an environment variable name is compiled in"
+    assert b"scatter16" not in blob, "the experimental 16-bit staging kernel is in the shipped library"
+    src = "".join(open(os.path.join(ROOT, "drjit_b200", "csrc", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "drjit_b200", "csrc")) if f.endswith((".cu", ".cuh", ".h")))
+    outside = re.sub(r"#if defined\(DRJIT_B200_EXPERIMENTS\).*?#e(?:lse|ndif)", "", src, flags=re.S)
+    assert "getenv" not in outside, "getenv() outside an experiments-only block"
+
+
 def test_python_binding_covers_every_symbol():
     from drjit_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_symbols()

@@ -136,17 +136,19 @@ def _worker(rank, world, port, n):
         # mkperm: global histogram + rank-major stable order == oracle permutation
         B = 37
         keys = capi.fmix32(n) % np.uint32(B)
-        perm, hist, ghist = sh.mkperm(torch.from_numpy(keys[lo:hi].view(np.int32).copy()), B, lo)
-        assert np.array_equal(ghist.numpy(), np.bincount(keys, minlength=B))
-        gathered = [torch.zeros_like(hist) for _ in range(world)]
-        dist.all_gather(gathered, hist)
-        exp_perm, _, _ = capi.block_mkperm(keys, n, B)
-        bucket_start = np.cumsum(ghist.numpy()) - ghist.numpy()
+        res = sh.mkperm(torch.from_numpy(keys[lo:hi].view(np.int32).copy()), B, lo)
+        perm, hist = res.perm, res.hist
+        ghist = np.bincount(keys, minlength=B)
+        exp_perm, exp_off, exp_unique = capi.block_mkperm(keys, n, B)
+        # the table of non-empty buckets describes the GLOBAL array: identical to the single-array oracle table
+        assert res.table.shape[0] == exp_unique
+        assert np.array_equal(res.table.numpy().astype(np.uint32).reshape(-1), exp_off[:4 * exp_unique])
         local_start = np.cumsum(hist.numpy()) - hist.numpy()
-        for b in range(B):
-            before = sum(int(g[b]) for g in gathered[:rank])
+        rank_base = res.rank_base.numpy().view(np.uint32)
+        for b in range(B):      # rank r's slice of bucket b sits at rank_base[b] of the stable global permutation
             mine = perm.numpy().view(np.uint32)[local_start[b]:local_start[b] + int(hist[b])]
-            assert np.array_equal(mine, exp_perm[bucket_start[b] + before: bucket_start[b] + before + int(hist[b])])
+            assert np.array_equal(mine, exp_perm[rank_base[b]: rank_base[b] + int(hist[b])])
+        assert int(hist.sum()) == hi - lo and ghist.sum() == n
 
         # scatter-add with all-reduced bins; dot
         f = capi.unit_f32(n)
@@ -159,6 +161,45 @@ def _worker(rank, world, port, n):
         assert abs(float(d[0]) - float(np.dot(f.astype(np.float64), f))) < 1e-4 * n
     finally:
         dist.destroy_process_group()
+
+
+def _worker_tiny(rank, world, port):
+    """n < world: the trailing shard is empty and must contribute the identity (no size-mismatched
+    collective, no uninitialised total)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from drjit_b200.dist import Sharded
+        from drjit_b200.ops import ReduceOp, VarType
+        sh = Sharded(rank=rank, world=world, group=dist.group.WORLD, local=OracleLocal())
+        n = 1
+        lo, hi = sh.shard_range(n)
+        assert (hi - lo) == (1 if rank == 0 else 0)
+        u = np.array([41], np.uint32)
+        ut = torch.from_numpy(u[lo:hi].view(np.int32).copy())
+        for op, exp in ((ReduceOp.Add, 41), (ReduceOp.Min, 41), (ReduceOp.Max, 41), (ReduceOp.Mul, 41)):
+            assert sh.reduce(op, ut, vt=VarType.UInt32).numpy().view(np.uint32)[0] == exp, op
+        got = sh.prefix_sum(ut).numpy().view(np.uint32)
+        assert got.size == hi - lo and (got.size == 0 or got[0] == 0)
+        local, off = sh.prefix_reduce_offsets(ReduceOp.Add, ut)
+        assert int(off.numpy().view(np.uint32)[0]) == (0 if rank == 0 else 41)
+        assert sh.all(torch.ones(hi - lo, dtype=torch.uint8)) is True
+        assert sh.any(torch.zeros(hi - lo, dtype=torch.uint8)) is False
+        out, counts = sh.compress(torch.ones(hi - lo, dtype=torch.uint8), lo)
+        assert counts == [1, 0]
+        res = sh.mkperm(torch.zeros(hi - lo, dtype=torch.int32), 4, lo)
+        assert res.table.tolist() == [[0, 0, 1, 0]] and int(res.hist.sum()) == hi - lo
+        f = torch.full((hi - lo,), 2.0)
+        assert float(sh.dot(f, f)[0]) == 4.0
+        bins = sh.scatter_add(torch.zeros(4), f, torch.zeros(hi - lo, dtype=torch.int32))
+        assert bins.tolist() == [2.0, 0.0, 0.0, 0.0]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_empty_trailing_shard_gloo_world2():
+    mp.spawn(_worker_tiny, args=(2, 29400 + (os.getpid() % 90)), nprocs=2, join=True)
 
 
 @pytest.mark.parametrize("n", [100_003, 4096])

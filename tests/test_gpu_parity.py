@@ -653,6 +653,34 @@ def test_scatter_reduce_other_ops(op):
             assert np.array_equal(got, exp), (vt, op, mode)
 
 
+@pytest.mark.parametrize("vt", ["f32", "f64"])
+def test_scatter_minmax_negative_zero(vt):
+    """-0.0 has the sign bit set, so the reference sends it down the unsigned-atomic path
+    (`setp.ge.s32` on the bit pattern, src/cuda_scatter.cpp:98-105): min(-5, -0.0) = -5,
+    max(-5, -0.0) = -0.0, min(+0.0, -0.0) = -0.0, max(-0.0, +0.0) = +0.0 -- the IEEE total order,
+    compared bit for bit."""
+    npt = NP[vt]
+    bits = np.uint32 if vt == "f32" else np.uint64
+    init = np.array([-5.0, -5.0, 0.0, -0.0, 3.0, -1e-30, -0.0, 7.0], npt)
+    val = np.array([-0.0] * 6 + [0.0, -0.0], npt)
+    idx = np.arange(8, dtype=np.uint32)
+
+    def total_order_key(a):     # monotone map of IEEE bit patterns to unsigned integers
+        b = a.view(bits).astype(np.uint64)
+        sign = np.uint64(1) << np.uint64(8 * a.itemsize - 1)
+        allones = np.uint64((1 << (8 * a.itemsize)) - 1)
+        return np.where(b & sign, (~b) & allones, b | sign)
+
+    for op in ("min", "max"):
+        ka, kb = total_order_key(init), total_order_key(val)
+        take_val = (kb < ka) if op == "min" else (kb > ka)
+        exp = np.where(take_val, val, init).astype(npt)
+        for mode in (ReduceMode.Direct, ReduceMode.Local):
+            got = to_np(dr.scatter_reduce(OPS[op], to_dev(init, vt), to_dev(val, vt), to_dev(idx, "u32"),
+                                          mode=mode, vt=VT[vt]), vt)
+            assert np.array_equal(got.view(bits), exp.view(bits)), (vt, op, mode, got, exp)
+
+
 @pytest.mark.parametrize("op", ["add", "min", "max"])
 @pytest.mark.parametrize("misalign", [0, 1])
 def test_scatter_reduce_f16(op, misalign):

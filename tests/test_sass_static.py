@@ -17,7 +17,8 @@ pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobj
 
 SCAN = "_ZN3djb20prefix_reduce_kernelIjNS_5OpAddELb0ELb1ELj8ELj3ELj2EEEvNS_12PrefixParamsE"
 COMPRESS = "_ZN3djb15compress_kernelILj8ELj1ELj3EEEvNS_14CompressParamsE"
-SUM = "_ZN3djb25block_reduce_chunk_kernelIfNS_5OpAddELb0ELb1EEEvPKT_S4_PS2_PNS_3AccIS2_E4typeEPjjjjj"
+SUM = "_ZN3djb25block_reduce_chunk_kernelIfNS_5OpAddELb0ELb1ELb0EEEvPKT_S4_PS2_PNS_3AccIS2_E4typeEPjjjjjNS_7PeerCtxEj"
+SUM_PEER = SUM.replace("ELb0ELb1ELb0EEE", "ELb0ELb1ELb1EEE")
 MKPERM_SCATTER = "_ZN3djb26mkperm_tile_scatter_kernelILj1024ELj%uEEEvNS_16MkpermTileParamsE"
 MKPERM_HIST = "_ZN3djb23mkperm_tile_hist_kernelILj1024ELj48EEEvNS_16MkpermTileParamsE"
 MKPERM_STABLE = "_ZN3djb33mkperm_tile_scatter_stable_kernelILj1024ELj8EEEvNS_16MkpermTileParamsE"
@@ -61,6 +62,16 @@ def test_mkperm_tile_kernels(kernel):
     assert re.search(r"\bATOMS", b), "no shared atomics"
     assert re.search(r"\bUBLKPF", b), "no L2 bulk prefetch"
     assert re.search(r"\bLDG\.E\.\S*128", b), "keys are not read with 128-bit loads"
+
+
+def test_fused_reduction_exchanges_over_peer_memory():
+    """The sharded reduction publishes its partial and spins on the flags inside the same kernel:
+    system-scope release stores / acquire loads, and no such code in the single-GPU instantiation."""
+    b = sass(SUM_PEER)
+    assert re.search(r"\bSTG?\.E\.\S*STRONG\.SYS", b), "no system-scope release store"
+    assert re.search(r"\bLDG?\.E\.\S*STRONG\.SYS", b), "no system-scope acquire load"
+    assert re.search(r"\bMEMBAR\.\S*SYS", b), "no system-scope fence"
+    assert not re.search(r"\bMEMBAR\.\S*SYS", sass(SUM))
 
 
 def test_stable_mkperm_ranks_with_ballots():
