@@ -81,7 +81,8 @@ def test_launch_hook_brackets_every_primitive_call():
     try:
         x = torch.ones(1 << 16, device="cuda")
         dr.sum(x)
-        dr.block_reduce(ReduceOp.Add, x[:0], 1)
+        # size == 0 is a no-op in the library: the hook still sees the call, with zero launches
+        lib.drjit_b200_block_reduce(None, int(VarType.Float32), int(ReduceOp.Add), 0, 1, None, None)
     finally:
         lib.drjit_b200_set_launch_hook(None, None)
     assert calls == [(0, 1, 1 << 16, 0, 0x1234), (1, 1, 1 << 16, 1, 0x1234),
@@ -129,7 +130,6 @@ def test_cuda_graph_capture_and_replay():
             side.synchronize()
         g.replay()
         torch.cuda.synchronize()
-        un = capi.fmix32(n, start=seed) if "start" in capi.fmix32.__code__.co_varnames else None
         # reference results from the same library outside the graph (parity with the oracle is covered elsewhere)
         exp_total = ops.block_reduce(ReduceOp.Add, f, n)
         exp_scan = ops.block_prefix_reduce(ReduceOp.Add, u, n, True, False, vt=VarType.UInt32)
@@ -140,4 +140,3 @@ def test_cuda_graph_capture_and_replay():
         assert c == int(exp_cnt.item()) and torch.equal(idx[:c], exp_idx[:c])
         assert torch.equal(perm, exp_perm) and torch.equal(hist, exp_hist)
         assert int(hist.sum().item()) == n and c == int(m.sum().item())
-        del un
