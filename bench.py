@@ -7,19 +7,26 @@ One "step" = one pass of the primitive suite over synthetic fmix32 inputs reside
     sum f32 2^28 | block_reduce(Add,256) f32 2^28 | dot f32 2^28 | exclusive prefix_sum u32 2^30 |
     compress 2^30 (50 % dense) | block_mkperm 2^26 keys x 4096 buckets | scatter_add f32 2^28 -> 2^20 bins
 
-value = algorithmic bytes of the whole suite / device time of one step (GB/s), inputs larger
-than L2 (no flush needed). With --gpus N every rank holds one shard of the sizes above (the
-global arrays are N times larger: "weak" scaling, rank r owns the contiguous index range
-[r*n, (r+1)*n)); NCCL is used only for the combine messages.
+value = algorithmic bytes of the whole suite / device time of one step (GB/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
+--gpus N (one rank per GPU, torchrun): STRONG scaling -- the global arrays keep the sizes above
+and rank r owns the contiguous index range [r*n/N, (r+1)*n/N) (north_star: "2^30-element mask
+sharded across 1/2/4/8"). The combine step of every primitive (a scalar, N counts, a bucket
+histogram, the 4 MB bin array) runs INSIDE the primitive's kernel over peer-mapped NVLink windows
+(drjit_b200/csrc/comm.cuh); the same suite over NCCL collectives is timed beside it
+(`nccl_path_ms`). After the timed region one untimed pass is verified against torch-computed
+invariants on every rank ("verified"). --weak gives every rank a full-size shard instead; a short
+weak-scaling run is also appended to the strong-scaling line (`weak_scaling`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--weak] [--scale S]
 
 --impl reference times the reference's own CPU implementation of the path (the unmodified
-drjit-core LLVM-backend primitives built into oracle/_ref) on the host cores.
+drjit-core LLVM-backend primitives built into oracle/_ref) on the host cores at the same sizes.
 --scale S shrinks every array by 2^S (debugging only; the JSON says so).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,18 +38,19 @@ sys.path.insert(0, ROOT)
 
 METRIC = "achieved HBM GB/s & % peak: reduce/scan/compress/mkperm @2^28, 1/2/4/8 GPU"
 
-# name -> (log2 elements, algorithmic bytes per element)   [SURVEY.md section 8d / BASELINE.md 2c]
+# name, log2 elements, algorithmic bytes per element [SURVEY.md section 8d / BASELINE.md 2c], kernel
 SUITE = [
-    ("sum_f32", 28, 4.0),
-    ("block_reduce256_f32", 28, 4.0 + 4.0 / 256),
-    ("dot_f32", 28, 8.0),
-    ("prefix_sum_u32", 30, 8.0),
-    ("compress_u8", 30, 3.0),          # 1 + 4 * density, density = 0.5
-    ("mkperm_4096", 26, 12.0),
-    ("scatter_add_f32", 28, 8.0),
+    ("sum_f32", 28, 4.0, "block_reduce_chunk_kernel<f32,Add>"),
+    ("block_reduce256_f32", 28, 4.0 + 4.0 / 256, "block_reduce_group_kernel<f32,Add,16 lanes>"),
+    ("dot_f32", 28, 8.0, "block_reduce_chunk_kernel<f32,Add,dot>"),
+    ("prefix_sum_u32", 30, 8.0, "prefix_reduce_kernel<u32,Add>"),
+    ("compress_u8", 30, 3.0, "compress_kernel<8,1,3>"),          # 1 + 4 * density, density = 0.5
+    ("mkperm_4096", 26, 12.0, "mkperm_tile_hist_kernel + column/bucket scan kernels + mkperm_tile_scatter_kernel<1024,48>"),
+    ("scatter_add_f32", 28, 8.0, "scatter_reduce_kernel<f32,Add>"),
 ]
 BINS_LOG2 = 20
 BUCKETS = 4096
+L2_BYTES = 126 << 20
 
 
 def measured_peaks():
@@ -119,57 +127,90 @@ class ClockSampler:
                 "samples": len(sel), "window": window}
 
 
-def measured_traffic(kernel, elements):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when the capture
-    was taken at another size."""
+def measured_traffic(primitive, elements):
+    """DRAM bytes per call from the committed `ncu --set full` captures (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum over the primitive's kernels); None when no
+    capture exists at this size."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            e = json.load(f)[kernel]
+            e = json.load(f)[primitive]
         return float(e["dram_bytes_per_launch"]) if int(e["elements"]) == int(elements) else None
     except (OSError, KeyError, ValueError):
         return None
 
 
+def workload_text():
+    return ("primitive suite: sum/block_reduce(256)/dot f32 2^28, exclusive prefix_sum u32 2^30, "
+            "compress u8 2^30 (50%), block_mkperm 2^26 x 4096 buckets, scatter_add f32 2^28 -> 2^20 bins")
+
+
+def workload_config(args, weak=False, distinct=False):
+    n = args.gpus
+    if weak:
+        sharding = (f"weak: {n} rank(s), each owning a full-size shard (global arrays {n}x larger; "
+                    "compress indices are global mod 2^32)")
+    else:
+        sharding = (f"strong: global sizes as stated, rank r of {n} owns the contiguous range [r*n/{n}, (r+1)*n/{n})")
+    if n > 1:
+        sharding += ("; combine steps fused into the primitives' kernels over peer-mapped NVLink windows (no NCCL on "
+                     "the data path); prefix_sum in shard-offset form (local scan + per-shard offset, like the "
+                     "compress / mkperm offsets), materialised form reported alongside")
+    l2 = ("no flush: every input array a primitive reads is larger than the 126 MB L2, or -- when the per-rank shards "
+          "approach the L2 size (N >= 4) -- every primitive reads its own input arrays and one step touches > 2 GB per "
+          "rank between re-uses, so no input is L2-resident when its primitive starts")
+    return {"workload": workload_text(), "sharding": sharding, "l2": l2, "scale_shift": args.scale}
+
+
 # ------------------------------------------------------------------------------------------
 #  reference arm: the unmodified reference's CPU primitives (oracle/_ref), all host threads
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_log2):
-    """Times the suite on a bounded sample (2^sample_log2 elements per primitive, 2^(sample-2)
-    for mkperm) with the reference LLVM backend. Returns (GB/s, per-primitive dict, cores)."""
+def cpu_reference_run(steps, warmup, scale):
+    """Times the suite at the BASELINE sizes (shrunk by 2^scale) with the reference LLVM-backend
+    primitives on host arrays, all host threads. scatter_add: the reference JIT-compiles that
+    loop, which the stub libLLVM of oracle/ref_build cannot do -> oracle.c's restatement of the
+    reference's ReduceMode::Expand scheme (one private copy of the bins per worker + fold) with the
+    same thread count. Returns (GB/s, per-primitive dict, cores, seconds per step)."""
+    import ctypes
+
     import numpy as np
     from oracle import capi, ref
 
     cores = os.cpu_count() or 1
     L = ref.lib(cuda=False, llvm=True)
     L.ref_llvm_set_thread_count(cores)
-    n = 1 << sample_log2
-    nk = 1 << max(10, sample_log2 - 2)
+    size = {name: 1 << max(10, lg - scale) for name, lg, _, _ in SUITE}
+    bpe = {name: b for name, _, b, _ in SUITE}
+    bins = 1 << max(4, BINS_LOG2 - scale)
+    n, ns, nk = size["sum_f32"], size["prefix_sum_u32"], size["mkperm_4096"]
     x = capi.unit_f32(n); y = capi.unit_f32(n, xor=0x9E3779B9)
-    u = capi.fmix32(n); m = capi.mask_u8(n, 128); keys = capi.fmix32(nk, mask=BUCKETS - 1)
+    u = capi.fmix32(ns); m = capi.mask_u8(ns, 128); keys = capi.fmix32(nk, mask=BUCKETS - 1)
+    sidx = capi.fmix32(n, xor=0x85EBCA6B, mask=bins - 1)
 
-    import ctypes
     vp = ctypes.c_void_p
     P = lambda a: a.ctypes.data_as(vp)  # noqa: E731
-    out_f = np.zeros(max(1, n // 256), np.float32); out_u = np.empty(n, np.uint32)
-    idx = np.empty(n, np.uint32); perm = np.empty(nk, np.uint32); offs = np.zeros(4 * BUCKETS + 1, np.uint32)
+    out_f = np.zeros(max(1, n // 256), np.float32); out_u = np.empty(ns, np.uint32)
+    idx = np.empty(ns, np.uint32); perm = np.empty(nk, np.uint32); offs = np.zeros(4 * BUCKETS + 1, np.uint32)
     dot_out = np.zeros(1, np.float32)
+    bins_a = np.zeros(bins, np.float32); scratch = np.empty(cores * bins, np.float32)
     VT_F32, VT_U32, ADD, LLVM = 14, 8, 1, 2
 
+    def scatter():
+        bins_a[:] = 0
+        capi.scatter_add_expand_f32(bins_a, x, sidx, cores, scratch)
+
     prims = {
-        "sum_f32": (n * 4.0, lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, n, P(x), P(out_f)), L.ref_sync())),
-        "block_reduce256_f32": (n * (4.0 + 4.0 / 256), lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, 256, P(x), P(out_f)), L.ref_sync())),
-        "dot_f32": (n * 8.0, lambda: L.ref_reduce_dot(LLVM, VT_F32, P(x), P(y), n, P(dot_out))),
-        "prefix_sum_u32": (n * 8.0, lambda: (L.ref_block_prefix_reduce(LLVM, VT_U32, ADD, n, n, 1, 0, P(u), P(out_u)), L.ref_sync())),
-        "compress_u8": (n * 3.0, lambda: L.ref_compress(LLVM, P(m), n, P(idx))),
-        "mkperm_4096": (nk * 12.0, lambda: (L.ref_block_mkperm(LLVM, P(keys), nk, nk, BUCKETS, P(perm), P(offs)), L.ref_sync())),
-        # scatter_add: the reference CPU path needs its LLVM JIT (ReduceMode::Expand), which the
-        # stub libLLVM cannot provide -> reported as n/a and left out of the CPU aggregate.
+        "sum_f32": lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, n, P(x), P(out_f)), L.ref_sync()),
+        "block_reduce256_f32": lambda: (L.ref_block_reduce(LLVM, VT_F32, ADD, n, 256, P(x), P(out_f)), L.ref_sync()),
+        "dot_f32": lambda: L.ref_reduce_dot(LLVM, VT_F32, P(x), P(y), n, P(dot_out)),
+        "prefix_sum_u32": lambda: (L.ref_block_prefix_reduce(LLVM, VT_U32, ADD, ns, ns, 1, 0, P(u), P(out_u)), L.ref_sync()),
+        "compress_u8": lambda: L.ref_compress(LLVM, P(m), ns, P(idx)),
+        "mkperm_4096": lambda: (L.ref_block_mkperm(LLVM, P(keys), nk, nk, BUCKETS, P(perm), P(offs)), L.ref_sync()),
+        "scatter_add_f32": scatter,
     }
     times = {k: [] for k in prims}
     for it in range(warmup + steps):
-        for name, (_, fn) in prims.items():
+        for name, fn in prims.items():
             t0 = time.perf_counter()
             fn()
             dt = time.perf_counter() - t0
@@ -177,48 +218,318 @@ def cpu_reference_run(steps, warmup, sample_log2):
                 times[name].append(dt)
     per = {}
     tot_bytes = tot_time = 0.0
-    for name, (nbytes, _) in prims.items():
+    for name in prims:
         t = sum(times[name]) / len(times[name])
-        per[name] = {"GBps": nbytes / t / 1e9, "ms": t * 1e3}
+        nbytes = size[name] * bpe[name]
+        per[name] = {"elements": size[name], "GBps": nbytes / t / 1e9, "ms": t * 1e3}
         tot_bytes += nbytes; tot_time += t
-    per["scatter_add_f32"] = "n/a (reference CPU scatter needs the LLVM JIT)"
+    per["scatter_add_f32"]["kind"] = ("port: oracle.c restatement of the reference's ReduceMode::Expand scatter "
+                                      "(its LLVM JIT is not available); the other six are the unmodified reference")
     return tot_bytes / tot_time / 1e9, per, cores, tot_time
+
+
+def cpu_sample_text(scale, cores):
+    sz = ("the full BASELINE sizes (2^28 f32 / 2^30 u32 / 2^30 u8 / 2^26 keys / 2^28 -> 2^20 bins)" if scale == 0
+          else f"the BASELINE sizes shrunk by 2^{scale}")
+    return (f"whole suite (7 primitives) at {sz}, host arrays, unmodified reference LLVM-backend primitives "
+            f"(oracle/_ref) on {cores} threads; scatter_add through oracle.c's Expand-mode restatement")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_log2 = 26
-    value, per, cores, step_s = cpu_reference_run(args.steps, max(1, min(args.warmup, 2)), sample_log2)
-    sample = (f"suite without scatter_add at 2^{sample_log2} elements per primitive (mkperm 2^{sample_log2 - 2} keys), "
-              f"host arrays, unmodified reference LLVM-backend primitives, {cores} threads")
+    value, per, cores, step_s = cpu_reference_run(args.steps, max(1, min(args.warmup, 2)), args.scale)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": sample},
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32/u32/u8",
+        "data": "synthetic (fmix32)", "config": workload_config(args, weak=args.weak),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "reference",
+                         "sample": cpu_sample_text(args.scale, cores)},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "primitives": per, "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args):
-    return {"workload": "primitive suite: sum/block_reduce(256)/dot f32 2^28, exclusive prefix_sum u32 2^30, "
-                        "compress u8 2^30 (50%), block_mkperm 2^26 x 4096 buckets, scatter_add f32 2^28 -> 2^20 bins",
-            "sharding": f"{args.gpus} rank(s), each owning one contiguous shard of the sizes above (global arrays "
-                        f"are {args.gpus}x larger; compress indices are global mod 2^32); NCCL only for combine messages"
-                        + ("; prefix_sum in shard-offset form (local scan + per-shard offset, like the compress / mkperm "
-                           "offsets), materialised form reported alongside" if args.gpus > 1 else ""),
-            "l2": "every input array > 126 MB L2 (no flush needed)",
-            "scale_shift": args.scale}
+# ------------------------------------------------------------------------------------------
+#  NUMA placement of a rank (pinned staging buffers are first-touched after this)
+# ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Restricts this process to the CPUs of the NUMA node its GPU hangs off, so that pinned
+    buffers allocated afterwards are node-local. Returns a description (or why it did nothing)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return "unknown (nvidia-smi gave no bus id)"
+        bus = bus[-12:] if len(bus) > 12 else bus          # 00000000:1B:00.0 -> 0000:1b:00.0
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return f"node {node} (no affinity change)"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node}, {len(cpus)} cpus"
+    except (OSError, ValueError, subprocess.SubprocessError) as e:
+        return f"unknown ({type(e).__name__})"
 
 
 # ------------------------------------------------------------------------------------------
 #  GPU arm
 # ------------------------------------------------------------------------------------------
+class Workload:
+    """Device-resident shard of every input plus the output buffers of one rank."""
+
+    def __init__(self, torch, ops, ddist, dev, rank, world, scale, weak):
+        self.size = {name: 1 << (lg - scale) for name, lg, _, _ in SUITE}       # global (strong) / per rank (weak)
+        self.bins = 1 << max(4, BINS_LOG2 - scale)
+        self.weak, self.rank, self.world = weak, rank, world
+
+        def rng(name, align=1):
+            n = self.size[name]
+            if weak:
+                return rank * n, (rank + 1) * n
+            b = ddist.shard_bounds(n, world, align)
+            return b[rank], b[rank + 1]
+
+        self.range = {"sum_f32": rng("sum_f32", 256), "prefix_sum_u32": rng("prefix_sum_u32", 64),
+                      "compress_u8": rng("compress_u8", 64), "mkperm_4096": rng("mkperm_4096", 64),
+                      "scatter_add_f32": rng("scatter_add_f32", 64)}
+        self.range["block_reduce256_f32"] = self.range["dot_f32"] = self.range["sum_f32"]
+        lo, hi = self.range["sum_f32"]
+        # shards that approach the L2 size: one input array per primitive (see config.l2)
+        self.distinct = (hi - lo) * 4 < 4 * L2_BYTES
+
+        def f32(lo, hi, xor=0):
+            t = torch.empty(hi - lo, dtype=torch.float32, device=dev)
+            return ops.fill_fmix32(t, 1, start=lo, xor=xor)
+
+        self.x = f32(lo, hi)
+        self.x_br = f32(lo, hi) if self.distinct else self.x
+        self.x_dot = f32(lo, hi) if self.distinct else self.x
+        self.y = f32(lo, hi, xor=0x9E3779B9)
+        lo, hi = self.range["prefix_sum_u32"]
+        self.u = ops.fill_fmix32(torch.empty(hi - lo, dtype=torch.int32, device=dev), 0, start=lo)
+        self.u_out = torch.empty_like(self.u)
+        lo, hi = self.range["compress_u8"]
+        self.mask = ops.fill_fmix32(torch.empty(hi - lo, dtype=torch.uint8, device=dev), 2, start=lo, and_=128)
+        self.c_out = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+        lo, hi = self.range["mkperm_4096"]
+        self.keys = ops.fill_fmix32(torch.empty(hi - lo, dtype=torch.int32, device=dev), 0, start=lo, and_=BUCKETS - 1)
+        self.perm = torch.empty_like(self.keys)
+        lo, hi = self.range["scatter_add_f32"]
+        self.sidx = ops.fill_fmix32(torch.empty(hi - lo, dtype=torch.int32, device=dev), 0, start=lo,
+                                    xor=0x85EBCA6B, and_=self.bins - 1)
+        self.sval = f32(lo, hi) if (self.distinct or (lo, hi) != self.range["sum_f32"]) else self.x
+        self.bins_t = torch.zeros(self.bins, dtype=torch.float32, device=dev)
+        self.br_out = torch.empty((self.x.numel() + 255) // 256, dtype=torch.float32, device=dev)
+
+    def elements(self, name):
+        """elements all ranks process together"""
+        return self.size[name] * (self.world if self.weak else 1)
+
+    def total_bytes(self):
+        return sum(self.elements(name) * b for name, _, b, _ in SUITE)
+
+
+def make_prims(wl, sh, ops, ReduceOp, VarType, results):
+    """The seven primitives of one step as closures (public API of drjit_b200)."""
+    world = sh.world
+    zero = b"\0\0\0\0"
+
+    def p_sum():
+        results["sum"] = sh.reduce(ReduceOp.Add, wl.x)
+
+    def p_block_reduce():
+        results["br"] = sh.block_reduce(ReduceOp.Add, wl.x_br, 256, out=wl.br_out)   # block-aligned shards: no exchange
+
+    def p_dot():
+        results["dot"] = sh.dot(wl.x_dot, wl.y)
+
+    def p_prefix():
+        if world > 1:   # shard-offset form (see module docstring / DESIGN.md section 5)
+            results["scan"] = sh.prefix_reduce_offsets(ReduceOp.Add, wl.u, vt=VarType.UInt32, out=wl.u_out)
+        else:
+            results["scan"] = (ops.block_prefix_reduce(ReduceOp.Add, wl.u, wl.u.numel(), True, False,
+                                                       vt=VarType.UInt32, out=wl.u_out), None)
+
+    def p_compress():
+        results["count"] = sh.compress(wl.mask, wl.range["compress_u8"][0] & 0xFFFFFFFF, out=wl.c_out)
+
+    def p_mkperm():
+        if world > 1:
+            results["mkperm"] = sh.mkperm(wl.keys, BUCKETS, wl.range["mkperm_4096"][0] & 0xFFFFFFFF, perm=wl.perm)
+        else:           # the seam function jit_var_call_reduce calls (call.cpp:1324): pinned table + count
+            results["mkperm"] = ops.block_mkperm(wl.keys, wl.keys.numel(), BUCKETS, perm=wl.perm, raw_table=True)
+
+    def p_scatter():
+        ops.memset(wl.bins_t, zero)
+        results["bins"] = sh.scatter_add(wl.bins_t, wl.sval, wl.sidx)
+
+    return [("sum_f32", p_sum), ("block_reduce256_f32", p_block_reduce), ("dot_f32", p_dot),
+            ("prefix_sum_u32", p_prefix), ("compress_u8", p_compress), ("mkperm_4096", p_mkperm),
+            ("scatter_add_f32", p_scatter)]
+
+
+def verify(torch, dist, wl, results, rank, world, dev):
+    """One untimed pass checked against torch-computed invariants on every rank (bit-exact for the
+    integer results, 1e-6 * log2 N relative for f32 sums). Returns {primitive: bool}, AND-ed over ranks."""
+    ok = {}
+    M32 = 0xFFFFFFFF
+
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def gather(t):
+        if world == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    CH = 1 << 24
+    # ---- sum / dot (f32, tolerance) and block_reduce
+    n_glob = wl.elements("sum_f32")
+    tol = 1e-6 * math.log2(max(n_glob, 2))
+    exp = float(allsum(torch.sum(wl.x, dtype=torch.float64).reshape(1))[0])
+    got = float(results["sum"].cpu()[0])
+    ok["sum_f32"] = abs(got - exp) <= tol * abs(exp)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    for lo in range(0, wl.x_dot.numel(), CH):
+        acc += torch.sum(wl.x_dot[lo:lo + CH].double() * wl.y[lo:lo + CH].double())
+    exp = float(allsum(acc)[0])
+    got = float(results["dot"].cpu()[0])
+    ok["dot_f32"] = abs(got - exp) <= tol * abs(exp)
+    nb = wl.x_br.numel() // 256
+    expb = torch.sum(wl.x_br[:nb * 256].view(nb, 256), dim=1, dtype=torch.float64)
+    gotb = results["br"][:nb].double()
+    ok["block_reduce256_f32"] = bool(torch.all((gotb - expb).abs() <= 1e-6 * 8 * expb.abs().clamp_min(1.0)))
+    del expb, gotb
+
+    # ---- exclusive prefix sum (u32, bit-exact): global[i] = offset + local[i]
+    local, offset = results["scan"]
+    shard_total = torch.sum(wl.u.long() & M32).reshape(1) & M32
+    lower = int(gather(shard_total)[:rank].sum().item()) & M32 if world > 1 else 0
+    good = True
+    if offset is not None:
+        good = (int(offset.cpu()[0]) & M32) == lower
+    carry = lower
+    for lo in range(0, wl.u.numel(), CH):
+        v = wl.u[lo:lo + CH].long() & M32
+        inc = torch.cumsum(v, 0)
+        expc = (inc - v + carry) & M32
+        gotc = ((local[lo:lo + CH].long() & M32) + (lower if offset is not None else 0)) & M32
+        good = good and bool(torch.equal(expc, gotc))
+        carry = (carry + int(inc[-1].item())) & M32
+    ok["prefix_sum_u32"] = good
+
+    # ---- compress: counts of all ranks + exact index list of this shard
+    c_out, counts = results["count"]
+    base = wl.range["compress_u8"][0]
+    my = torch.sum(wl.mask != 0).reshape(1)
+    exp_counts = [int(c) for c in gather(my).flatten().cpu().tolist()]
+    good = [int(c) for c in counts] == exp_counts
+    pos = 0
+    for lo in range(0, wl.mask.numel(), CH):
+        nz = (torch.nonzero(wl.mask[lo:lo + CH]).flatten() + (lo + base)) & M32
+        good = good and bool(torch.equal(c_out[pos:pos + nz.numel()].long() & M32, nz))
+        pos += nz.numel()
+    ok["compress_u8"] = good and pos == exp_counts[rank]
+
+    # ---- mkperm: permutation of the shard, keys non-decreasing along it, histogram, global table
+    res = results["mkperm"]
+    kbase = wl.range["mkperm_4096"][0]
+    nk = wl.keys.numel()
+    hist_exp = torch.bincount(wl.keys.long(), minlength=BUCKETS)
+    allh = gather(hist_exp)
+    gsize = allh.sum(0)
+    gstart = torch.cumsum(gsize, 0) - gsize
+    ids = torch.nonzero(gsize).flatten()
+    table_exp = torch.stack([ids, gstart[ids], gsize[ids], torch.zeros_like(ids)], 1).cpu()
+    if world > 1:
+        perm, table = res.perm, res.table
+        good = bool(torch.equal(res.hist.long() & M32, hist_exp))
+        good = good and bool(torch.equal(res.rank_base.long() & M32, (gstart + allh[:rank].sum(0)) & M32))
+    else:
+        perm, offsets, unique = res
+        table = (offsets[:4 * unique].view(-1, 4).to(torch.int64) & M32)
+        good = True
+    p = ((perm.long() & M32) - kbase)
+    good = good and bool(p.min() >= 0) and bool(p.max() < nk) and bool(torch.all(torch.bincount(p, minlength=nk) == 1))
+    k = wl.keys[p]
+    good = good and bool(torch.all(k[1:] >= k[:-1]))
+    ok["mkperm_4096"] = good and bool(torch.equal(table.cpu(), table_exp))
+    del p, k
+
+    # ---- scatter_add: bins against an f64 accumulation of the global array
+    expb = torch.zeros(wl.bins, dtype=torch.float64, device=dev)
+    for lo in range(0, wl.sval.numel(), CH):
+        expb.index_add_(0, wl.sidx[lo:lo + CH].long(), wl.sval[lo:lo + CH].double())
+    allsum(expb)
+    ok["scatter_add_f32"] = bool(torch.all((results["bins"].double() - expb).abs() <= 1e-5 * expb.abs().clamp_min(1.0)))
+
+    flags = torch.tensor([int(bool(ok[name])) for name, _, _, _ in SUITE], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    return {name: bool(int(f)) for (name, _, _, _), f in zip(SUITE, flags.cpu().tolist())}
+
+
+def time_suite(torch, dist, dr, prims, steps, world, dev):
+    """Times exactly `steps` steps (barrier + synchronize on both sides, device events, MAX over
+    ranks). Returns (ms per step, [ms per primitive], launches, (t0, t1) monotonic)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prims]
+          for _ in range(steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    dr.launch_count(reset=True)
+    t0 = time.monotonic()
+    start.record()
+    for k in range(steps):
+        for i, (_, fn) in enumerate(prims):
+            ev[k][i][0].record()
+            fn()
+            ev[k][i][1].record()
+    end.record()
+    barrier()
+    t1 = time.monotonic()
+    launches = dr.launch_count()
+    total_ms = start.elapsed_time(end)
+    per_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(steps)) / steps for i in range(len(prims))]
+    t = torch.tensor([total_ms] + per_ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]) / steps, [float(v) for v in t[1:]], launches, (t0, t1)
+
+
+def primitive_table(wl, per_ms, peak, world):
+    out = {}
+    for (name, _, bpe, _), ms in zip(SUITE, per_ms):
+        el = wl.elements(name)
+        gbs = el * bpe / (ms * 1e-3) / 1e9
+        out[name] = {"elements": el, "ms": round(ms, 4), "GBps": round(gbs, 1),
+                     "Gelem_per_s": round(el / (ms * 1e-3) / 1e9, 2),
+                     "frac_of_peak_per_gpu": round(gbs / (peak * world), 4)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,14 +538,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=0, help="shrink every array by 2^SCALE (debug)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: every rank owns a full-size shard")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the verified pass (profiler runs only; the JSON says so)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the NCCL-path, materialised-scan and weak-scaling side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
         run_reference_arm(args)
         return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single rank)"
 
     import torch
     import torch.distributed as dist
@@ -243,95 +562,33 @@ def main():
     from drjit_b200 import ReduceOp, VarType, ops
     from drjit_b200 import dist as ddist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    sh = ddist.Sharded(rank=rank, world=world, group=dist.group.WORLD if world > 1 else None)
+        comm = ddist.PeerComm.from_process_group(dist.group.WORLD, device=dev, bulk_bytes=8 << 20)
+    group = dist.group.WORLD if world > 1 else None
+    sh = ddist.Sharded(rank=rank, world=world, group=group, comm=comm)          # product path (fused combine)
+    sh_nccl = ddist.Sharded(rank=rank, world=world, group=group)                # library-collective baseline
 
     peak, peak_src = measured_peaks()
-    S = args.scale
-    size = {name: 1 << (lg - S) for name, lg, _ in SUITE}
-    bpe = {name: b for name, _, b in SUITE}
-    bins = 1 << max(4, BINS_LOG2 - S)
-
-    # ---- shard-resident synthetic inputs (generated on the device) -------------------------
-    def shard(n):
-        """Weak scaling: rank r owns elements [r*n, (r+1)*n) of a global array of world*n entries."""
-        return rank * n, (rank + 1) * n
-
-    lo_f, hi_f = shard(size["sum_f32"])
-    x = torch.empty(hi_f - lo_f, dtype=torch.float32, device=dev); ops.fill_fmix32(x, 1, start=lo_f)
-    y = torch.empty(hi_f - lo_f, dtype=torch.float32, device=dev); ops.fill_fmix32(y, 1, start=lo_f, xor=0x9E3779B9)
-    lo_u, hi_u = shard(size["prefix_sum_u32"])
-    u = torch.empty(hi_u - lo_u, dtype=torch.int32, device=dev); ops.fill_fmix32(u, 0, start=lo_u)
-    u_out = torch.empty_like(u)
-    lo_m, hi_m = shard(size["compress_u8"])
-    mask = torch.empty(hi_m - lo_m, dtype=torch.uint8, device=dev); ops.fill_fmix32(mask, 2, start=lo_m, and_=128)
-    c_out = torch.empty(hi_m - lo_m, dtype=torch.int32, device=dev)
-    lo_k, hi_k = shard(size["mkperm_4096"])
-    keys = torch.empty(hi_k - lo_k, dtype=torch.int32, device=dev); ops.fill_fmix32(keys, 0, start=lo_k, and_=BUCKETS - 1)
-    perm = torch.empty_like(keys)
-    lo_s, hi_s = shard(size["scatter_add_f32"])
-    sidx = torch.empty(hi_s - lo_s, dtype=torch.int32, device=dev); ops.fill_fmix32(sidx, 0, start=lo_s, xor=0x85EBCA6B, and_=bins - 1)
-    sval = x if (lo_s, hi_s) == (lo_f, hi_f) else torch.empty(hi_s - lo_s, dtype=torch.float32, device=dev)
-    if sval is not x:
-        ops.fill_fmix32(sval, 1, start=lo_s)
-    bins_t = torch.zeros(bins, dtype=torch.float32, device=dev)
-    br_out = torch.empty((x.numel() + 255) // 256, dtype=torch.float32, device=dev)
-
+    wl = Workload(torch, ops, ddist, dev, rank, world, args.scale, args.weak)
     results = {}
-
-    def p_sum():
-        results["sum"] = sh.reduce(ReduceOp.Add, x)
-
-    def p_block_reduce():
-        results["br"] = ops.block_reduce(ReduceOp.Add, x, 256, out=br_out)   # block-aligned shards: no exchange
-
-    def p_dot():
-        results["dot"] = sh.dot(x, y)
-
-    def p_prefix():
-        # N > 1: shard-offset form (local scan + per-shard offset, the representation the compress /
-        # mkperm offsets use as well; dist.py). The materialised form is timed separately below.
-        if world > 1:
-            results["scan"] = sh.prefix_reduce_offsets(ReduceOp.Add, u, vt=VarType.UInt32, out=u_out)
-        else:
-            results["scan"] = sh.prefix_sum(u, vt=VarType.UInt32, out=u_out)
-
-    def p_compress():
-        results["count"] = sh.compress(mask, lo_m & 0xFFFFFFFF, out=c_out)
-
-    def p_mkperm():
-        results["mkperm"] = sh.mkperm(keys, BUCKETS, lo_k & 0xFFFFFFFF, perm=perm)
-
-    def p_scatter():
-        bins_t.zero_()
-        results["bins"] = sh.scatter_add(bins_t, sval, sidx)
-
-    prims = [("sum_f32", p_sum), ("block_reduce256_f32", p_block_reduce), ("dot_f32", p_dot),
-             ("prefix_sum_u32", p_prefix), ("compress_u8", p_compress), ("mkperm_4096", p_mkperm),
-             ("scatter_add_f32", p_scatter)]
-    total_bytes = world * sum(size[n] * bpe[n] for n, _ in prims)   # all ranks
+    prims = make_prims(wl, sh, ops, ReduceOp, VarType, results)
+    total_bytes = wl.total_bytes()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(events=None):
-        for i, (name, fn) in enumerate(prims):
-            if events is not None:
-                events[i][0].record()
+    def one_step(pr):
+        for _, fn in pr:
             fn()
-            if events is not None:
-                events[i][1].record()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -342,7 +599,7 @@ def main():
     # W warm-up steps, padded (same count on every rank) so that the clocks are sampled under
     # this load for >= 1 s before the timed region starts
     for _ in range(args.warmup):
-        one_step()
+        one_step(prims)
     barrier()
     elapsed = time.monotonic() - t_load
     extra = 0 if elapsed >= 1.0 else min(2000, int((1.0 - elapsed) / max(elapsed / args.warmup, 1e-4)) + 1)
@@ -351,56 +608,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         extra = int(t.item())
     for _ in range(extra):
-        one_step()
-    barrier()
-    dr.launch_count(reset=True)
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prims]
-          for _ in range(args.steps)]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_timed0 = time.monotonic()
-    start.record()
-    for k in range(args.steps):
-        one_step(ev[k])
-    end.record()
-    barrier()
-    t_timed1 = time.monotonic()
-    launches = dr.launch_count()
+        one_step(prims)
+
+    ms_per_step, per_ms, launches, (t_timed0, t_timed1) = time_suite(torch, dist, dr, prims, args.steps, world, dev)
     clocks = sampler.stop(t_load, t_timed0, t_timed1) if rank == 0 else None
-
-    total_ms = start.elapsed_time(end)
-    per_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps
-              for i in range(len(prims))]
-    t = torch.tensor([total_ms] + per_ms, dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t[0]); per_ms = [float(v) for v in t[1:]]
-    ms_per_step = total_ms / args.steps
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    primitives = primitive_table(wl, per_ms, peak, world)
 
-    primitives = {}
-    for (name, _), ms in zip(prims, per_ms):
-        gbs = world * size[name] * bpe[name] / (ms * 1e-3) / 1e9
-        primitives[name] = {"elements": world * size[name], "ms": round(ms, 4), "GBps": round(gbs, 1),
-                            "Gelem_per_s": round(world * size[name] / (ms * 1e-3) / 1e9, 2),
-                            "frac_of_peak_per_gpu": round(gbs / (peak * world), 4)}
+    # ---- one untimed, verified pass on every rank ------------------------------------------
+    checked, verified = {}, None
+    if not args.no_verify:
+        one_step(prims)
+        barrier()
+        checked = verify(torch, dist, wl, results, rank, world, dev)
+        verified = all(checked.values())
+        if not verified:
+            raise SystemExit(f"bench.py: verification failed on the {world}-rank run: {checked}")
 
-    # ---- informational (NOT part of `value`): the sharded scan in materialised form (every element
-    # carries the global value: one more read pass over the shard, 12 B/element) next to the
-    # shard-offset form timed above (8 B/element)
-    if world > 1:
+    # ---- side measurements (NOT part of `value`) --------------------------------------------
+    side_steps = max(3, min(args.steps, 20))
+    weak_scaling = None
+    if world > 1 and not args.no_extras:
+        # (1) the same suite with the combine steps over NCCL collectives instead of peer memory
+        res2 = {}
+        pr2 = make_prims(wl, sh_nccl, ops, ReduceOp, VarType, res2)
+        one_step(pr2)
+        ms2, per2, _, _ = time_suite(torch, dist, dr, pr2, side_steps, world, dev)
+        for (name, _, _, _), ms in zip(SUITE, per2):
+            primitives[name]["nccl_path_ms"] = round(ms, 4)
+        primitives["_suite"] = {"fused_ms": round(ms_per_step, 4), "nccl_path_ms": round(ms2, 4)}
+        # (2) the scan in materialised form (every element carries the global value: 12 B/element)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sh.prefix_sum(u, vt=VarType.UInt32, out=u_out)
+        sh.prefix_sum(wl.u, vt=VarType.UInt32, out=wl.u_out)
         barrier()
         a.record()
-        for _ in range(args.steps):
-            sh.prefix_sum(u, vt=VarType.UInt32, out=u_out)
+        for _ in range(side_steps):
+            sh.prefix_sum(wl.u, vt=VarType.UInt32, out=wl.u_out)
         b.record()
         barrier()
-        t = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+        t = torch.tensor([a.elapsed_time(b) / side_steps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
-        gbs = world * size["prefix_sum_u32"] * 8.0 / (ms * 1e-3) / 1e9
+        gbs = wl.elements("prefix_sum_u32") * 8.0 / (ms * 1e-3) / 1e9
         primitives["prefix_sum_u32"]["form"] = "shard-offset (local scan + per-shard offset)"
         primitives["prefix_sum_u32"]["materialised_form"] = {
             "ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_peak_per_gpu": round(gbs / (peak * world), 4),
@@ -409,32 +658,58 @@ def main():
     # ---- end-to-end: host buffers through the public API, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank,
-                      dict(x=x, y=y, u=u, mask=mask, keys=keys, sidx=sidx, sval=sval),
-                      dict(u_out=u_out, c_out=c_out, perm=perm, bins_t=bins_t, br_out=br_out),
-                      prims, results, total_bytes)
+        e2e = run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, total_bytes)
+        if e2e is not None:
+            e2e["numa"] = numa
+
+    # ---- weak scaling beside the strong-scaling headline -------------------------------------
+    if world > 1 and not args.weak and not args.no_extras:
+        del wl, prims
+        results.clear()
+        torch.cuda.empty_cache()
+        wlw = Workload(torch, ops, ddist, dev, rank, world, args.scale, True)
+        resw = {}
+        prw = make_prims(wlw, sh, ops, ReduceOp, VarType, resw)
+        for _ in range(3):
+            one_step(prw)
+        msw, perw, _, _ = time_suite(torch, dist, dr, prw, side_steps, world, dev)
+        weak_scaling = {"value": round(wlw.total_bytes() / (msw * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(msw, 4),
+                        "steps": side_steps, "note": f"every rank owns a full-size shard (global arrays {world}x larger)",
+                        "primitives_ms": {name: round(ms, 4) for (name, _, _, _), ms in zip(SUITE, perw)}}
+        wl_distinct = False
+    else:
+        wl_distinct = wl.distinct
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
+            comm.destroy()
             dist.destroy_process_group()
         return
 
-    # dominant kernel for the roofline object: the single-pass scan (largest share of the step)
-    scan = primitives["prefix_sum_u32"]
-    roofline = {"bound": "hbm", "kernel": "prefix_reduce_kernel<u32,Add> (exclusive prefix_sum, 2^30 elements per rank)",
-                "achieved": scan["GBps"] / world, "peak": peak, "unit": "GB/s",
-                "frac": round(scan["GBps"] / world / peak, 4),
-                "traffic": measured_traffic("prefix_reduce_kernel", size["prefix_sum_u32"]), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": size["prefix_sum_u32"] * 8.0}
+    # per-primitive rooflines; `roofline` = the kernel with the largest share of the step
+    rooflines = []
+    for (name, lg, bpe, kernel), ms in zip(SUITE, per_ms):
+        p = primitives[name]
+        per_gpu_elems = p["elements"] // world
+        rooflines.append({"primitive": name, "kernel": kernel, "bound": "hbm",
+                          "achieved": round(p["GBps"] / world, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(p["GBps"] / world / peak, 4),
+                          "traffic": measured_traffic(name, per_gpu_elems),
+                          "algorithmic_bytes_per_launch": per_gpu_elems * bpe,
+                          "share_of_step": round(ms / sum(per_ms), 4)})
+    roofline = dict(max(rooflines, key=lambda r: r["share_of_step"]))
+    roofline["peak_source"] = peak_src
+    roofline["note"] = ("dominant kernel = largest share of the step's device time (CUDA events around every primitive "
+                        "call); all seven are listed in `rooflines`")
 
     cpu_baseline = None
     if not args.no_cpu:
         try:
-            v, per, cores, _ = cpu_reference_run(2, 1, 24)
+            v, per, cores, _ = cpu_reference_run(2, 1, args.scale)
             cpu_baseline = {"value": round(v, 2), "unit": "GB/s", "cores": cores, "kind": "reference",
-                            "sample": "suite without scatter_add at 2^24 elements per primitive (mkperm 2^22 keys), "
-                                      "unmodified reference LLVM-backend CPU primitives (oracle/_ref), all host threads",
-                            "primitives": {k: (round(p["GBps"], 2) if isinstance(p, dict) else p) for k, p in per.items()}}
+                            "sample": cpu_sample_text(args.scale, cores) + "; 2 timed steps after 1 warm-up",
+                            "primitives": {k: round(p["GBps"], 2) for k, p in per.items()}}
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"unavailable: {e}"}
@@ -442,26 +717,35 @@ def main():
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32/u8", "data": "synthetic (fmix32)",
-        "config": workload_config(args), "frac_of_hbm_peak": round(value / (peak * world), 4),
-        "primitives": primitives, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-        "gpu_launches": launches, "clocks": clocks,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32/u32/u8",
+        "data": "synthetic (fmix32)", "config": workload_config(args, weak=args.weak, distinct=wl_distinct),
+        "frac_of_hbm_peak": round(value / (peak * world), 4), "verified": verified, "verified_primitives": checked,
+        "primitives": primitives, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "weak_scaling": weak_scaling, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        comm.destroy()
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, prims, results, total_bytes):
+def run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, total_bytes):
     """Same suite, but every step first copies the step's inputs host->device from pinned
     memory and afterwards reads every primitive's result back to the host."""
     from drjit_b200 import ReduceOp, VarType
-    host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in inputs.items() if k != "sval" or v is not inputs["x"]}
+    # a user uploads x once and runs sum / block_reduce / dot on it (uploads come between the
+    # primitives here, so L2 residency is not a concern as it is in the device-timed run)
+    saved = (wl.x_br, wl.x_dot)
+    wl.x_br = wl.x_dot = wl.x
+    inputs = dict(x=wl.x, y=wl.y, u=wl.u, mask=wl.mask, keys=wl.keys, sidx=wl.sidx, sval=wl.sval)
+    outputs = dict(u_out=wl.u_out, c_out=wl.c_out, perm=wl.perm, bins_t=wl.bins_t, br_out=wl.br_out)
+    host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in inputs.items() if k != "sval" or v is not wl.x}
     for k, h in host_in.items():
         h.copy_(inputs[k])
     host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outputs.items()}
     h2d = sum(h.numel() * h.element_size() for h in host_in.values())
-    steps = max(2, min(args.steps, 3))
+    steps = max(2, args.steps)
 
     # Pipelined step: uploads, kernels and downloads run on three streams (PCIe is full duplex and
     # the GPU has separate copy engines per direction), chained by events per primitive. The
@@ -490,6 +774,7 @@ def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, p
     cs = (n_u // SCAN_CHUNKS + 3) // 4 * 4 if n_u >= 64 * SCAN_CHUNKS else n_u
     bounds = [(lo, min(lo + cs, n_u)) for lo in range(0, n_u, cs)]
     carry = [torch.zeros(1, dtype=u_dev.dtype, device=dev), torch.zeros(1, dtype=u_dev.dtype, device=dev)]
+    offset = torch.zeros(1, dtype=u_dev.dtype, device=dev)
 
     def scan_chunked(up_u):
         moved = 0
@@ -502,12 +787,11 @@ def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, p
                 s_out.wait_event(done)
                 host_out["u_out"][lo:hi].copy_(u_res[lo:hi], non_blocking=True)
             moved += (hi - lo) * u_res.element_size()
-        if world > 1:       # shard-offset form: exclusive scan of the gathered shard totals
-            totals = sh._all_gather(carry[len(bounds) & 1])
-            offs = ops.block_prefix_reduce(ReduceOp.Add, totals, totals.numel(), True, False, vt=VarType.UInt32)
-            results["scan"] = (u_res, offs[rank:rank + 1])
+        if world > 1:       # shard-offset form: exclusive fold of the shard totals over the lower ranks
+            sh.fold_scalar(ReduceOp.Add, carry[len(bounds) & 1], offset, lower=True, vt=VarType.UInt32)
+            results["scan"] = (u_res, offset)
         else:
-            results["scan"] = u_res
+            results["scan"] = (u_res, None)
         return moved
 
     def step():
@@ -545,7 +829,7 @@ def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, p
                         host_out[k].copy_(v, non_blocking=True); d2h += v.numel() * v.element_size()
         for k in ("sum", "dot"):
             results[k].cpu(); d2h += 4
-        if isinstance(results["scan"], tuple):      # shard-offset form: the offset travels with the scan
+        if results["scan"][1] is not None:          # shard-offset form: the offset travels with the scan
             results["scan"][1].cpu(); d2h += 4
         s_out.synchronize()
         return d2h
@@ -568,12 +852,17 @@ def run_e2e(args, torch, dist, dr, ops, sh, dev, world, rank, inputs, outputs, p
     if world > 1:
         dist.barrier()
     dt = (time.perf_counter() - t0) / steps
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t[0])
-    return {"value": round(total_bytes / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": int(h2d) * world,
-            "d2h_bytes_per_step": int(d2h) * world, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt = float(tmax[0])
+    h2d_all, d2h_all = int(t[1]), int(t[2])
+    wl.x_br, wl.x_dot = saved
+    return {"value": round(total_bytes / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d_all,
+            "d2h_bytes_per_step": d2h_all, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
+            "pcie_GBps": {"h2d": round(h2d_all / dt / 1e9, 1), "d2h": round(d2h_all / dt / 1e9, 1),
+                          "note": "all ranks together, per direction, averaged over the step"},
             "note": "per rank: pinned host inputs -> device, suite through the public API, every result "
                     "(scalars, block sums, scan, index list, permutation, bins) -> pinned host; uploads, "
                     "kernels and downloads pipelined on three streams, the scan fed in 8 pieces through its carry form"}

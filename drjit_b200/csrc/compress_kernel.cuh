@@ -48,6 +48,21 @@ struct CompressParams {
 
 constexpr uint32_t kCompWindowLoads = 3;                     // carry window: grids of up to 768 CTAs
 constexpr uint32_t kComp2RowStride = kCompRowSlots;          // u16 entries per warp staging row
+constexpr uint32_t kCompBulkSlots = kCompRowSlots + 8;       // u32 entries per warp staging row, bulk copy-out
+                                                             // (shifted by the destination's offset inside 16 bytes)
+
+/// How the indices of a warp row leave the SM
+enum : uint32_t {
+    kCopyLsu = 0,    // 16-bit staging entries, LDS.U16 + STG.32 per index
+    kCopyBulk = 1    // 32-bit staging entries, one shared -> global bulk copy (TMA engine) per row
+};
+
+/// Dynamic shared memory of an instantiation: the input stage(s) + the copy-out staging rows
+template <uint32_t ROWS, uint32_t STAGES, uint32_t COPY>
+constexpr uint32_t compress_smem_bytes() {
+    return STAGES * kCompThreads * ROWS * kCompUnit +
+           (COPY == kCopyBulk ? kCompWarps * 2 * kCompBulkSlots * 4 : kCompWarps * kComp2RowStride * 2);
+}
 
 /// bit k <- (byte k of the 16-byte unit is non-zero)
 __device__ __forceinline__ uint32_t unit_mask16(const uint4 &v) {
@@ -62,6 +77,14 @@ __device__ __forceinline__ uint32_t unit_mask16(const uint4 &v) {
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((uint16_t) v) : "memory");
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
@@ -74,7 +97,9 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
-template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS>
+/// COPY: kCopyLsu / kCopyBulk. BASE512: p.index_base is a multiple of 512, so that the index of an
+/// entry is the OR of (row base | lane * 16 | position nibble) -- no add per entry (kCopyBulk only).
+template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t COPY = kCopyLsu, bool BASE512 = true>
 __global__ void __launch_bounds__(kCompThreads, MIN_CTAS)
 compress_kernel(const CompressParams p) {
     static_assert(ROWS % 2 == 0, "rows are ranked in pairs");
@@ -83,8 +108,8 @@ compress_kernel(const CompressParams p) {
     constexpr bool STAGED = STAGES > 0;
     constexpr uint32_t NS = STAGED ? STAGES : 1;
     static_assert(TILE <= 65536, "tile-local offsets are staged as 16-bit values");
-    extern __shared__ __align__(128) uint8_t stage_mem[];       // STAGES x TILE
-    __shared__ __align__(16) uint16_t row_stage[kCompWarps][kComp2RowStride];
+    extern __shared__ __align__(128) uint8_t stage_mem[];       // STAGES x TILE, then the copy-out staging rows
+    uint8_t *const row_stage_mem = stage_mem + (size_t) STAGES * TILE;
     __shared__ uint32_t lut[256];           // byte -> positions of its set bits, one nibble each, ascending
     __shared__ uint64_t full_bar[NS];
     __shared__ uint32_t wcnt[4][kCompWarps];    // per-warp counts of tiles it-1 .. it+2
@@ -198,7 +223,9 @@ compress_kernel(const CompressParams p) {
     if (warp == 0) { publish_aggregate(0); publish_aggregate(1); }
 
     const uint32_t lane16 = lane * kCompUnit;
-    const uint32_t stg_addr = smem_addr(row_stage[warp]);
+    const uint32_t stg_addr = smem_addr(row_stage_mem) +
+                              warp * (COPY == kCopyBulk ? 2 * kCompBulkSlots * 4 : kComp2RowStride * 2);
+    uint32_t bulk_par = 0;              // kCopyBulk: which of the warp's two staging rows is written next
 
     for (uint32_t it = 0;; ++it) {
         const uint64_t tile64 = tile_of(it);
@@ -273,6 +300,53 @@ compress_kernel(const CompressParams p) {
                 // 64-bit nibble stream: positions of the set bits of m, ascending
                 const uint32_t lo = lut[m & 0xffu], hi = lut[m >> 8] + 0x88888888u;
                 const uint64_t q = (uint64_t) lo | ((uint64_t) hi << (4 * __popc(m & 0xffu)));
+                const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
+                if constexpr (COPY == kCopyBulk) {
+                    // Staging slot s of the row corresponds to dst[s - a], a = position of dst inside its
+                    // 16-byte line: the aligned middle of the row then leaves with ONE shared -> global
+                    // bulk copy issued by lane 0 (no LSU instruction per index), up to 3 + 3 entries at
+                    // the ragged ends with scalar stores. Two staging rows per warp: the copy of row k
+                    // reads its row while row k + 1 is being staged.
+                    const uint32_t a = ((uint32_t) (uintptr_t) dst >> 2) & 3u;
+                    const uint32_t buf = stg_addr + bulk_par * (kCompBulkSlots * 4);
+                    bulk_par ^= 1u;
+                    if (lane == 0) bulk_wait_read<1>();     // the copy issued two rows ago has read this row
+                    __syncwarp();
+                    const uint32_t base = BASE512 ? (idx_row | lane16) : idx_row + lane16;
+                    uint32_t wa = buf + 4 * (a + r);
+                    asm volatile("" : "+r"(wa));
+                    auto entry = [&](uint32_t nib) -> uint32_t {
+                        return BASE512 ? and_or(nib, 15u, base) : (nib & 15u) + base;
+                    };
+                    if (n > 64) {
+                        #pragma unroll
+                        for (uint32_t j = 0; j < kCompUnit; ++j)
+                            if (j < c)
+                                sts_u32(wa + 4 * j, entry((uint32_t) (q >> (4 * j))));
+                    } else {
+                        const uint32_t cmax = __reduce_max_sync(kFullMask, c);
+                        uint64_t qq = q;
+                        for (uint32_t j = 0; j < cmax; ++j, qq >>= 4)
+                            if (j < c)
+                                sts_u32(wa + 4 * j, entry((uint32_t) qq));
+                    }
+                    fence_proxy_async();                    // staged entries -> visible to the bulk copy engine
+                    __syncwarp();
+                    const uint32_t end = a + n, s0 = (a + 3u) & ~3u, s1 = end & ~3u;
+                    const bool body = s1 > s0;
+                    if (lane < 8 && lane >= a && lane < end && (!body || lane < s0))
+                        dst[lane - a] = lds_u32(buf + 4 * lane);
+                    if (body) {
+                        const uint32_t t = s1 + lane;
+                        if (lane < 3 && t < end)
+                            dst[t - a] = lds_u32(buf + 4 * t);
+                        if (lane == 0)
+                            bulk_store(dst - a + s0, buf + 4 * s0, (s1 - s0) * 4);
+                    }
+                    if (lane == 0) bulk_commit();
+                    dst += n;
+                    continue;
+                }
                 uint32_t wa = stg_addr + 2 * r;
                 asm volatile("" : "+r"(wa));      // (keeps ptxas from re-deriving the address per store)
                 if (n > 64) {
@@ -291,7 +365,6 @@ compress_kernel(const CompressParams p) {
                 __syncwarp();
                 // coalesced copy-out, 128 slots per round (a two-slots-per-lane LDS.32/STG.64
                 // variant was 18 % slower: profiles/r1f_sweep_compress_paired_copyout.txt)
-                const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
                 {   // (pointers and the remaining count are stepped explicitly: immediates only inside)
                     uint32_t *o = dst + lane;
                     uint32_t sa = stg_addr + 2 * lane;
@@ -313,6 +386,9 @@ compress_kernel(const CompressParams p) {
         }
         #pragma unroll
         for (uint32_t i = 0; i < PAIRS; ++i) { cur[i] = nxt[i]; nxt[i] = nxt2[i]; }
+    }
+    if constexpr (COPY == kCopyBulk) {
+        if (lane == 0) bulk_wait_read<0>();     // the staging rows must outlive the copies that read them
     }
 }
 

@@ -73,6 +73,22 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *gmem, uint32_t byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gmem), "r"(bytes) : "memory");
 }
 
+/// shared -> global bulk copy (SASS: UBLKCP.G.S); `bytes` multiple of 16, both addresses 16-byte
+/// aligned. Completion is tracked per thread through bulk groups (commit / wait below); the
+/// shared-memory source must have been written before a fence.proxy.async by its writers.
+__device__ __forceinline__ void bulk_store(void *gmem_dst, uint32_t smem_src_addr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gmem_dst), "r"(smem_src_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+/// Blocks until all but the N most recent bulk groups of this thread have finished READING their
+/// shared-memory source (the source may then be overwritten; the global writes may still be in flight)
+template <uint32_t N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+
 /// 128-bit shared-memory load
 __device__ __forceinline__ uint4 lds128(const void *p) {
     uint4 r;

@@ -213,6 +213,21 @@ class Sharded:
         allp = self._all_gather(part)
         return self.local.block_reduce(ReduceOp.Add, allp, allp.numel())
 
+    def fold_scalar(self, op, src, dst, lower=False, vt=None):
+        """dst[0] = fold over the ranks (``lower``: only the ranks below the caller, the carry of a
+        forward scan) of every rank's 1-element device tensor ``src``. Fused path: one tiny
+        peer-exchange kernel; collective path: all-gather + local fold."""
+        if self.comm is not None:
+            with torch.cuda.device(src.device):
+                self._check(self._lib.drjit_b200_comm_fold(self.comm.ptr, self._s(src), self._vt(src, vt), int(op),
+                                                           FOLD_LOWER if lower else FOLD_ALL, self._p(src), self._p(dst)))
+            return dst
+        allp = self._all_gather(src)
+        if lower:
+            allp = allp[:self.rank] if self.rank else _identity(op, src, vt)
+        dst.copy_(self.local.block_reduce(op, allp, allp.numel(), vt=vt))
+        return dst
+
     # ------------------------------------------------------------------ prefix sum
     def prefix_reduce(self, op, x, exclusive=True, vt=None, out=None):
         """Global prefix reduction, *materialised*: every element carries the global value. Rank r needs

@@ -262,22 +262,28 @@ def _pinned_offsets(bucket_count):
     return buf
 
 
-def block_mkperm(values, block_size, bucket_count, want_offsets=True):
+def block_mkperm(values, block_size, bucket_count, want_offsets=True, perm=None, raw_table=False):
     """dr.detail.block_mkperm(values, block_size, bucket_count) -> (perm, offsets | None).
 
     ``perm`` is a device array; it is complete in stream order (the call itself only waits for
     the bucket table, cuda_ts.cpp:953-967). ``offsets`` is a host int64 numpy-like tensor of
-    shape (unique, 4) with rows {bucket id, start, size, 0}, only for block_size == size."""
+    shape (unique, 4) with rows {bucket id, start, size, 0}, only for block_size == size.
+    ``perm``: optional preallocated result. ``raw_table=True`` returns (perm, pinned offsets
+    buffer, unique count) exactly as the seam function leaves them (what jit_var_call_reduce reads,
+    call.cpp:1324-1378) -- the buffer is reused by the next call."""
     v = _check_array(values, "values")
     if _vt(v) not in (VarType.UInt32, VarType.Int32):
         raise RuntimeError("drjit_b200: block_mkperm() expects 32-bit integer keys")
     n = v.numel()
-    perm = torch.empty(n, dtype=torch.int32, device=v.device)
+    if perm is None:
+        perm = torch.empty(n, dtype=torch.int32, device=v.device)
     unique = ctypes.c_uint32(0)
     offsets = _pinned_offsets(bucket_count) if (want_offsets and block_size == n and n > 0) else None
     with torch.cuda.device(v.device):
         check(lib.drjit_b200_block_mkperm(_stream(v), _ptr(v), n, block_size, bucket_count, _ptr(perm),
                                           _ptr(offsets), ctypes.byref(unique)))
+    if raw_table:
+        return perm, offsets, unique.value
     table = None
     if offsets is not None:
         table = offsets[:4 * unique.value].clone().view(-1, 4).to(torch.int64) & 0xFFFFFFFF

@@ -49,6 +49,7 @@ def lib():
         L.oracle_any.argtypes = [vp, u32]
         L.oracle_scatter_reduce.argtypes = [i32, i32, vp, u32, vp, vp, vp, u32, i32]
         L.oracle_memset.argtypes = [vp, u32, u32, vp]
+        L.oracle_scatter_add_expand_f32.argtypes = [vp, u32, vp, vp, u32, u32, vp]
         L.oracle_aggregate.argtypes = [vp, vp, u32]
         _lib = L
     return _lib
@@ -158,6 +159,16 @@ def scatter_reduce(vt, op, target, value, index, mask=None, acc64=False):
     m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
     _check(lib().oracle_scatter_reduce(VT[vt], OP[op], _p(target), target.size, _p(value), _p(index),
                                        _p(m), value.size, int(acc64)), "scatter_reduce")
+    return target
+
+
+def scatter_add_expand_f32(target, value, index, workers, scratch=None):
+    """In-place dr.scatter_add in the reference's CPU ReduceMode.Expand form (see oracle.c)."""
+    assert target.dtype == np.float32 and value.dtype == np.float32 and index.dtype == np.uint32
+    if scratch is None:
+        scratch = np.empty(workers * target.size, np.float32)
+    _check(lib().oracle_scatter_add_expand_f32(_p(target), target.size, _p(value), _p(index), value.size,
+                                               workers, _p(scratch)), "scatter_add_expand_f32")
     return target
 
 

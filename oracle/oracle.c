@@ -432,6 +432,58 @@ EXPORT int oracle_scatter_reduce(int vt, int op, void *target, uint32_t target_s
     }
 }
 
+/* scatter_add in ReduceMode::Expand, the mode the reference's LLVM backend picks for targets of
+ * up to 1 M entries (src/op.cpp:2845-2848, src/api.cpp:2073): the target is replicated once per
+ * worker (jitc_var_expand, src/var.cpp:2866-2931; replication factor = pool size,
+ * src/llvm_core.cpp:556-563), every worker scatters the 16384-element work units it picks up
+ * (src/llvm_core.cpp:67) into its private copy without atomics, and the copies are folded into
+ * copy 0 in worker order (reduce_expanded_impl, src/llvm_ts.cpp:1012-1028). The reference JIT-
+ * compiles the scatter loop; this is the same loop in C. Used only by bench.py's CPU baseline
+ * (the stub libLLVM of oracle/ref_build cannot JIT). Work units are dealt round-robin. */
+#include <pthread.h>
+struct expand_job { float *copies; const float *value; const uint32_t *index; uint32_t target_size, size, worker, workers; };
+static void *expand_scatter_worker(void *arg) {
+    struct expand_job *j = (struct expand_job *) arg;
+    float *t = j->copies + (size_t) j->worker * j->target_size;
+    const uint32_t unit = 16384;
+    for (uint64_t lo = (uint64_t) j->worker * unit; lo < j->size; lo += (uint64_t) j->workers * unit) {
+        uint64_t hi = lo + unit < j->size ? lo + unit : j->size;
+        for (uint64_t i = lo; i < hi; ++i)
+            t[j->index[i]] += j->value[i];
+    }
+    return NULL;
+}
+static void *expand_fold_worker(void *arg) {
+    struct expand_job *j = (struct expand_job *) arg;
+    const uint32_t unit = 16384;
+    for (uint64_t lo = (uint64_t) j->worker * unit; lo < j->target_size; lo += (uint64_t) j->workers * unit) {
+        uint64_t hi = lo + unit < j->target_size ? lo + unit : j->target_size;
+        for (uint32_t w = 1; w < j->workers; ++w)
+            for (uint64_t k = lo; k < hi; ++k)
+                j->copies[k] += j->copies[k + (size_t) w * j->target_size];
+    }
+    return NULL;
+}
+/* scratch: workers * target_size floats owned by the caller (allocated once, like the expanded
+ * variable that stays alive between kernel launches); indices must be < target_size. */
+EXPORT int oracle_scatter_add_expand_f32(float *target, uint32_t target_size, const float *value,
+                                         const uint32_t *index, uint32_t size, uint32_t workers,
+                                         float *scratch) {
+    if (workers == 0 || workers > 1024) return -1;
+    pthread_t th[1024]; struct expand_job jobs[1024];
+    memcpy(scratch, target, sizeof(float) * (size_t) target_size);
+    memset(scratch + target_size, 0, sizeof(float) * (size_t) target_size * (workers - 1));
+    for (int phase = 0; phase < 2; ++phase) {
+        for (uint32_t w = 0; w < workers; ++w) {
+            jobs[w] = (struct expand_job) { scratch, value, index, target_size, size, w, workers };
+            pthread_create(&th[w], NULL, phase == 0 ? expand_scatter_worker : expand_fold_worker, &jobs[w]);
+        }
+        for (uint32_t w = 0; w < workers; ++w) pthread_join(th[w], NULL);
+    }
+    memcpy(target, scratch, sizeof(float) * (size_t) target_size);
+    return 0;
+}
+
 /* memset_async: src/llvm_ts.cpp:215-263 / cuda_ts.cpp:129-183 (isize in {1,2,4,8}) */
 EXPORT int oracle_memset(void *ptr, uint32_t size, uint32_t isize, const void *src) {
     if (isize != 1 && isize != 2 && isize != 4 && isize != 8) return -1;

@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIR = os.path.join(_HERE, "_ref")
+# ORACLE_REF_DIR=oracle/_ref_b200 selects the build whose CUDA primitives are libdrjit_b200.so's
+# (oracle/ref_build `make b200`; tests/test_insitu_gpu.py runs in a subprocess with it)
+REF_DIR = os.environ.get("ORACLE_REF_DIR") or os.path.join(_HERE, "_ref")
 CUDA, LLVM = 1, 2
 
 _lib = None
@@ -29,7 +31,7 @@ def lib(cuda=False, llvm=True):
         if not available():
             raise RuntimeError("oracle/_ref is not built (run `make -C oracle`)")
         # The reference dlopens libLLVM; point it at the stub unless the user has a real one
-        os.environ.setdefault("DRJIT_LIBLLVM_PATH", os.path.join(REF_DIR, "libLLVM.so"))
+        os.environ.setdefault("DRJIT_LIBLLVM_PATH", os.path.join(_HERE, "_ref", "libLLVM.so"))
         L = ctypes.CDLL(os.path.join(REF_DIR, "libref_shim.so"))
         vp, u32, i32, i64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int64
         L.ref_last_error.restype = ctypes.c_char_p
@@ -45,6 +47,9 @@ def lib(cuda=False, llvm=True):
         L.ref_block_mkperm.argtypes = [i32, vp, u32, u32, u32, vp, vp]; L.ref_block_mkperm.restype = i64
         L.ref_reduce_dot.argtypes = [i32, i32, vp, vp, u32, vp]
         L.ref_scatter_reduce.argtypes = [i32, i32, i32, i32, vp, u32, vp, vp, u32]
+        if hasattr(L, "ref_kernel_history"):
+            L.ref_set_flag.argtypes = [u32, i32]
+            L.ref_kernel_history.argtypes = [vp, vp, vp, vp, u32]; L.ref_kernel_history.restype = u32
         _lib = L
     want = (2 if cuda else 0) | (4 if llvm else 0)
     if want & ~_backends:

@@ -9,6 +9,7 @@
 #include <drjit-core/jit.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <exception>
 
 #define SHIM extern "C" __attribute__((visibility("default")))
@@ -116,3 +117,27 @@ SHIM int ref_scatter_reduce(int backend, int vt, int op, int mode, void *target,
         jit_var_dec_ref(vr); jit_var_dec_ref(vv); jit_var_dec_ref(vi); jit_var_dec_ref(vm);
     });
 }
+
+/// JitFlag (jit.h:1680-1783), e.g. KernelHistory = 1 << 15, LaunchBlocking = 1 << 16
+SHIM void ref_set_flag(uint32_t flag, int enable) { jit_set_flag((JitFlag) flag, enable); }
+
+/// jit_kernel_history() (jit.h:2700-2736) flattened for ctypes: copies up to `max` entries
+/// (backend, KernelType, size, execution time in ms) and frees the list. Returns the entry count.
+SHIM uint32_t ref_kernel_history(uint32_t *backends, uint32_t *types, uint32_t *sizes, float *times,
+                                 uint32_t max) {
+    KernelHistoryEntry *data = jit_kernel_history();
+    uint32_t n = 0;
+    if (!data)
+        return 0;
+    for (KernelHistoryEntry *e = data; (uint32_t) e->backend; ++e) {
+        if (n < max) {
+            backends[n] = (uint32_t) e->backend; types[n] = (uint32_t) e->type;
+            sizes[n] = e->size; times[n] = e->execution_time;
+        }
+        ++n;
+        free(e->ir);
+    }
+    free(data);
+    return n;
+}
+SHIM void ref_kernel_history_clear() { jit_kernel_history_clear(); }

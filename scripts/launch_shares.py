@@ -14,8 +14,8 @@ ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = OrderedDict()
 for r in rows[1:]:
     name = re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("djb::", "")
-    if name.startswith("at::") or "fill_fmix32" in name:
-        continue
+    if name.startswith(("at::", "native::", "at_cuda_detail::", "cuda::")) or "fill_fmix32" in name:
+        continue        # torch kernels of bench.py's verification pass / input generation
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[iv]) / 1e3
 tot = sum(v[1] for v in agg.values())
 print("| kernel | launches | total us | us / launch | share of step (ncu) |\n|---|---|---|---|---|")

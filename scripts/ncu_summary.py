@@ -31,8 +31,12 @@ def main():
           "durations are under the profiler (cold caches, serialised) and are not bench values.\n")
     print("| report | kernel | grid x block | " + " | ".join(k for _, k in KEYS) + " | top stalls (pc samples) |")
     print("|---|---|---|" + "---|" * (len(KEYS) + 1))
-    for rep in sorted(glob.glob(os.path.join(d, "full_*.ncu-rep"))):
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    reps = sorted(glob.glob(os.path.join(d, "full_*.ncu-rep"))) or sorted(glob.glob(os.path.join(d, "full_*.csv")))
+    for rep in reps:
+        if rep.endswith(".csv"):      # raw page exported on the GPU box (the reports are too large to travel)
+            out = open(rep).read()
+        else:
+            out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         if len(rows) < 3:
             continue

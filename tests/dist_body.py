@@ -65,6 +65,13 @@ def check_rank(sh, rank, world, dev, n, buckets=4096, bins=1 << 12):
     got = sh.prefix_reduce(ReduceOp.Max, up(u64[lo:hi].view(np.int64)), exclusive=False, vt=VarType.UInt64)
     assert np.array_equal(got.cpu().numpy().view(np.uint64), exp)
 
+    # ---- fold of one scalar per rank (the e2e path folds the chunked scan's shard totals with it)
+    mine = torch.tensor([rank + 5], dtype=torch.int32, device=dev)
+    got = sh.fold_scalar(ReduceOp.Add, mine, torch.zeros(1, dtype=torch.int32, device=dev), vt=VarType.UInt32)
+    assert int(got.cpu()[0]) == sum(r + 5 for r in range(world))
+    got = sh.fold_scalar(ReduceOp.Add, mine, torch.zeros(1, dtype=torch.int32, device=dev), lower=True, vt=VarType.UInt32)
+    assert int(got.cpu()[0]) == sum(r + 5 for r in range(rank))
+
     # ---- compress: global indices, rank-order concatenation == oracle list
     m = capi.mask_u8(n, 128)
     out, counts = sh.compress(up(m[lo:hi]), lo)

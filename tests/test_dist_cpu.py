@@ -125,6 +125,11 @@ def _worker(rank, world, port, n):
         local, off = sh.prefix_reduce_offsets(ReduceOp.Add, ut)
         assert np.array_equal((local.numpy().view(np.uint32) + off.numpy().view(np.uint32)[0]).astype(np.uint32), exp)
 
+        # fold of one scalar per rank (all ranks / only the lower ones)
+        mine = torch.tensor([rank + 5], dtype=torch.int32)
+        assert int(sh.fold_scalar(ReduceOp.Add, mine, torch.zeros(1, dtype=torch.int32))[0]) == sum(r + 5 for r in range(world))
+        assert int(sh.fold_scalar(ReduceOp.Add, mine, torch.zeros(1, dtype=torch.int32), lower=True)[0]) == sum(r + 5 for r in range(rank))
+
         # compress: global indices, rank-order concatenation == oracle list
         m = capi.mask_u8(n, 128)
         out, counts = sh.compress(torch.from_numpy(m[lo:hi].copy()), lo)
