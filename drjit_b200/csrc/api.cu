@@ -136,6 +136,11 @@ DRJIT_B200_API int drjit_b200_mkperm_sharded(void *stream, const uint32_t *value
     return primitive(DRJIT_B200_KT_MKPERM, size, stream, [&] { djb::mkperm_sharded(S(stream), values, size, bucket_count, index_base, perm, hist_dev); });
 }
 
+DRJIT_B200_API int drjit_b200_sort(void *stream, int vt, uint32_t size, int descending, const void *keys,
+                                   void *keys_out, uint32_t *index_out) {
+    return primitive(DRJIT_B200_KT_SORT, size, stream, [&] { djb::sort(S(stream), vt, size, descending != 0, keys, keys_out, index_out); });
+}
+
 DRJIT_B200_API int drjit_b200_poke(void *stream, void *dst, const void *src, uint32_t size) {
     return primitive(DRJIT_B200_KT_POKE, 1, stream, [&] { djb::poke(S(stream), dst, src, size); });
 }

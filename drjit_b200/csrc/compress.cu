@@ -21,12 +21,12 @@ namespace djb {
 
 constexpr uint32_t kCompRowsBig = 8, kCompRowsSmall = 2;
 
-template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS>
+template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t COPY = kCopyLsu, bool BASE512 = true>
 static void launch_compress(cudaStream_t stream, CompressParams &p, Scratch &scratch) {
     constexpr uint32_t TILE = kCompThreads * ROWS * kCompUnit;
     const DeviceProps &dev = device_props();
-    auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS>;
-    constexpr uint32_t smem = STAGES * TILE;
+    auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS, COPY, BASE512>;
+    constexpr uint32_t smem = compress_smem_bytes<ROWS, STAGES, COPY>();
     // (function attributes and occupancy are per device: one slot per device and instantiation)
     static std::atomic<int> occupancy_of[kMaxDevices] = {};
     int occupancy = occupancy_of[dev.device % kMaxDevices].load(std::memory_order_acquire);

@@ -54,14 +54,17 @@ constexpr uint32_t kCompBulkSlots = kCompRowSlots + 8;       // u32 entries per 
 /// How the indices of a warp row leave the SM
 enum : uint32_t {
     kCopyLsu = 0,    // 16-bit staging entries, LDS.U16 + STG.32 per index
-    kCopyBulk = 1    // 32-bit staging entries, one shared -> global bulk copy (TMA engine) per row
+    kCopyBulk = 1,   // 32-bit staging entries, one shared -> global bulk copy (TMA engine) per row
+    kCopyVec = 2,    // 32-bit staging entries aligned with the destination, LDS.128 + STG.128 per four indices
+    kCopyLsuPairs = 3 // kCopyLsu with the staging entries written two at a time (STS.32 of two 16-bit entries)
 };
 
 /// Dynamic shared memory of an instantiation: the input stage(s) + the copy-out staging rows
 template <uint32_t ROWS, uint32_t STAGES, uint32_t COPY>
 constexpr uint32_t compress_smem_bytes() {
     return STAGES * kCompThreads * ROWS * kCompUnit +
-           (COPY == kCopyBulk ? kCompWarps * 2 * kCompBulkSlots * 4 : kCompWarps * kComp2RowStride * 2);
+           (COPY == kCopyBulk ? kCompWarps * 2 * kCompBulkSlots * 4 :
+            COPY == kCopyVec ? kCompWarps * kCompBulkSlots * 4 : kCompWarps * (kComp2RowStride + 8) * 2);
 }
 
 /// bit k <- (byte k of the 16-byte unit is non-zero)
@@ -224,7 +227,8 @@ compress_kernel(const CompressParams p) {
 
     const uint32_t lane16 = lane * kCompUnit;
     const uint32_t stg_addr = smem_addr(row_stage_mem) +
-                              warp * (COPY == kCopyBulk ? 2 * kCompBulkSlots * 4 : kComp2RowStride * 2);
+                              warp * (COPY == kCopyBulk ? 2 * kCompBulkSlots * 4 :
+                                      COPY == kCopyVec ? kCompBulkSlots * 4 : (kComp2RowStride + 8) * 2);
     uint32_t bulk_par = 0;              // kCopyBulk: which of the warp's two staging rows is written next
 
     for (uint32_t it = 0;; ++it) {
@@ -301,17 +305,24 @@ compress_kernel(const CompressParams p) {
                 const uint32_t lo = lut[m & 0xffu], hi = lut[m >> 8] + 0x88888888u;
                 const uint64_t q = (uint64_t) lo | ((uint64_t) hi << (4 * __popc(m & 0xffu)));
                 const uint32_t idx_row = idx_warp + (2 * i + h) * kCompRowSlots;
-                if constexpr (COPY == kCopyBulk) {
-                    // Staging slot s of the row corresponds to dst[s - a], a = position of dst inside its
-                    // 16-byte line: the aligned middle of the row then leaves with ONE shared -> global
-                    // bulk copy issued by lane 0 (no LSU instruction per index), up to 3 + 3 entries at
-                    // the ragged ends with scalar stores. Two staging rows per warp: the copy of row k
-                    // reads its row while row k + 1 is being staged.
+                if constexpr (COPY == kCopyBulk || COPY == kCopyVec) {
+                    // 32-bit staging entries hold the final index. Staging slot s of the row corresponds
+                    // to dst[s - a], a = position of dst inside its 16-byte line, so that aligned groups of
+                    // four slots are aligned groups of four output words:
+                    //   kCopyVec : LDS.128 + STG.128 per four indices (3.5 LSU instructions per 128 indices
+                    //              instead of 8, no per-index add), scalar stores for up to 3 + 3 entries at
+                    //              the ragged ends;
+                    //   kCopyBulk: the aligned middle leaves with ONE shared -> global bulk copy issued by
+                    //              lane 0; two staging rows per warp so that the copy of row k reads its row
+                    //              while row k + 1 is being staged (measured slower: profiles/r4b_*).
                     const uint32_t a = ((uint32_t) (uintptr_t) dst >> 2) & 3u;
-                    const uint32_t buf = stg_addr + bulk_par * (kCompBulkSlots * 4);
-                    bulk_par ^= 1u;
-                    if (lane == 0) bulk_wait_read<1>();     // the copy issued two rows ago has read this row
-                    __syncwarp();
+                    uint32_t buf = stg_addr;
+                    if constexpr (COPY == kCopyBulk) {
+                        buf += bulk_par * (kCompBulkSlots * 4);
+                        bulk_par ^= 1u;
+                        if (lane == 0) bulk_wait_read<1>();     // the copy issued two rows ago has read this row
+                        __syncwarp();
+                    }
                     const uint32_t base = BASE512 ? (idx_row | lane16) : idx_row + lane16;
                     uint32_t wa = buf + 4 * (a + r);
                     asm volatile("" : "+r"(wa));
@@ -330,7 +341,8 @@ compress_kernel(const CompressParams p) {
                             if (j < c)
                                 sts_u32(wa + 4 * j, entry((uint32_t) qq));
                     }
-                    fence_proxy_async();                    // staged entries -> visible to the bulk copy engine
+                    if constexpr (COPY == kCopyBulk)
+                        fence_proxy_async();                    // staged entries -> visible to the bulk copy engine
                     __syncwarp();
                     const uint32_t end = a + n, s0 = (a + 3u) & ~3u, s1 = end & ~3u;
                     const bool body = s1 > s0;
@@ -340,16 +352,60 @@ compress_kernel(const CompressParams p) {
                         const uint32_t t = s1 + lane;
                         if (lane < 3 && t < end)
                             dst[t - a] = lds_u32(buf + 4 * t);
-                        if (lane == 0)
-                            bulk_store(dst - a + s0, buf + 4 * s0, (s1 - s0) * 4);
+                        if constexpr (COPY == kCopyBulk) {
+                            if (lane == 0)
+                                bulk_store(dst - a + s0, buf + 4 * s0, (s1 - s0) * 4);
+                        } else {
+                            // groups of four slots [s0 / 4, s1 / 4): lane takes group s0 / 4 + lane + 32 t
+                            const uint32_t g1 = s1 >> 2;
+                            uint32_t g = (s0 >> 2) + lane;
+                            uint4 *o = reinterpret_cast<uint4 *>(dst - a) + g;      // (dst - a is 16-byte aligned)
+                            uint32_t sa = buf + 16 * g;
+                            for (; g < g1; g += 32, o += 32, sa += 512) {
+                                uint4 v;
+                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+                                asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                                             :: "l"(o), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                            }
+                        }
                     }
-                    if (lane == 0) bulk_commit();
+                    if constexpr (COPY == kCopyBulk) {
+                        if (lane == 0) bulk_commit();
+                    } else {
+                        __syncwarp();                           // row copied out before the next one is staged
+                    }
                     dst += n;
                     continue;
                 }
                 uint32_t wa = stg_addr + 2 * r;
                 asm volatile("" : "+r"(wa));      // (keeps ptxas from re-deriving the address per store)
-                if (n > 64) {
+                if (COPY == kCopyLsuPairs && n > 64) {
+                    // Two entries per store: half as many shared-memory store instructions (and bank
+                    // conflict wavefronts) as the entry-wise loop below. A lane whose start r is odd
+                    // keeps its first entry for a 16-bit store and pairs up the rest from r + 1; a
+                    // lane with an odd number of paired entries writes one garbage half into the slot
+                    // after its last entry -- that slot is the (odd) start of the next non-empty lane,
+                    // whose 16-bit store comes AFTER all pair stores and puts the right entry there.
+                    const uint32_t odd = r & 1u;
+                    const uint32_t first = and_or((uint32_t) q, 15u, lane16);
+                    const uint32_t qlo = odd ? (uint32_t) (q >> 4) : (uint32_t) q,
+                                   qhi = odd ? (uint32_t) (q >> 36) : (uint32_t) (q >> 32);
+                    const uint32_t cp = c - odd * (c != 0);                 // entries that go out in pairs
+                    uint32_t wp = wa + 2 * odd;                             // 4-byte aligned
+                    asm volatile("" : "+r"(wp));
+                    const uint32_t lane2 = lane16 * 0x10001u;
+                    #pragma unroll
+                    for (uint32_t j = 0; j < kCompUnit / 2; ++j) {
+                        // byte j of the nibble stream = entries 2j, 2j+1 -> spread to two 16-bit fields
+                        const uint32_t xb = __byte_perm(qlo, qhi, 0x4440u | j);
+                        if (2 * j < cp)
+                            sts_u32(wp + 4 * j, and_or(xb * 0x1001u, 0x000f000fu, lane2));
+                    }
+                    __syncwarp();
+                    if (odd && c != 0)
+                        sts_u16(wa, first);
+                } else if (n > 64) {
                     #pragma unroll
                     for (uint32_t j = 0; j < kCompUnit; ++j)
                         if (j < c)

@@ -152,6 +152,8 @@ uint32_t block_mkperm(cudaStream_t s, const uint32_t *values, uint32_t size, uin
                       uint32_t bucket_count, uint32_t *perm, uint32_t *offsets);
 void mkperm_sharded(cudaStream_t s, const uint32_t *values, uint32_t size, uint32_t bucket_count,
                     uint32_t index_base, uint32_t *perm, uint32_t *hist_dev);
+void sort(cudaStream_t s, int vt, uint32_t size, bool descending, const void *keys, void *keys_out,
+          uint32_t *index_out);
 void poke(cudaStream_t s, void *dst, const void *src, uint32_t size);
 void aggregate(cudaStream_t s, void *dst, const drjit_b200_aggregation_entry *agg, uint32_t size);
 void scatter_reduce(cudaStream_t s, int vt, int op, int mode, void *target, uint32_t target_size,

@@ -290,6 +290,36 @@ def block_mkperm(values, block_size, bucket_count, want_offsets=True, perm=None,
     return perm, table
 
 
+# --------------------------------------------------------------------------- sort
+def _sort(value, descending, want_values, want_indices, vt=None):
+    x = _check_array(value)
+    t = _vt(x, vt)
+    if t not in (VarType.Int32, VarType.UInt32, VarType.Float32, VarType.Int64, VarType.UInt64, VarType.Float64):
+        raise RuntimeError(f"drjit_b200: sort(): unsupported type {t.name}")
+    n = x.numel()
+    values = torch.empty_like(x) if want_values else None
+    index = torch.empty(n, dtype=torch.int32, device=x.device) if want_indices else None
+    if n:
+        with torch.cuda.device(x.device):
+            check(lib.drjit_b200_sort(_stream(x), int(t), n, int(bool(descending)), _ptr(x), _ptr(values), _ptr(index)))
+    return values, index
+
+
+def sort(value, descending=False, vt=None):
+    """dr.sort(value, descending=False) for flat arrays (drjit/__init__.py:1784-1850)."""
+    return _sort(value, descending, True, False, vt)[0]
+
+
+def argsort(value, descending=False, vt=None):
+    """dr.argsort(value, descending=False): stable sorting permutation (UInt32 bits in an int32 tensor)."""
+    return _sort(value, descending, False, True, vt)[1]
+
+
+def sort_with_indices(value, descending=False, vt=None):
+    """(dr.sort(value), dr.argsort(value)) from one run of the passes."""
+    return _sort(value, descending, True, True, vt)
+
+
 # --------------------------------------------------------------------------- scatter-reduce
 def scatter_reduce(op, target, value, index, active=None, mode=ReduceMode.Auto, vt=None):
     """dr.scatter_reduce(op, target, value, index, active, mode): in-place on ``target``."""

@@ -263,6 +263,20 @@ DRJIT_B200_API int drjit_b200_scatter_reduce(void *stream, int vt, int op, int m
                                              const uint32_t *index, const uint8_t *mask,
                                              uint32_t size);
 
+/* dr.sort / dr.argsort, drjit/__init__.py:1698-1772 (`_radix_sort`: on the GPU four (eight for 64-bit
+ * types) 8-bit LSD passes, each a digit kernel + jit_block_mkperm + one gather per carried array).
+ * Here every pass moves the keys and the index payload itself (histogram launch + offsets launch +
+ * stable scatter launch, 20 bytes per element and pass instead of ~44; no permutation array, no
+ * gathers); the order-preserving transform of _to_ordinal_32/_64 (:1483-1520) is applied on the fly.
+ * keys: `size` entries of type vt in {i32, u32, f32, i64, u64, f64}; keys_out (same type, may be NULL):
+ * the sorted keys; index_out (u32, may be NULL): the stable sorting permutation (dr.argsort), i.e.
+ * keys_out[i] == keys[index_out[i]], equal keys in input order. Float order is that of the reference's
+ * ordinal transform: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN. keys_out must not alias
+ * keys. Asynchronous. Sorting of independent groups (block_size < size) is not implemented here:
+ * compose drjit_b200_block_mkperm passes as the reference does. */
+DRJIT_B200_API int drjit_b200_sort(void *stream, int vt, uint32_t size, int descending, const void *keys,
+                                   void *keys_out, uint32_t *index_out);
+
 /* ---- sharded / asynchronous forms (new: the reference is single-device) ---
  * Building blocks for one-process-per-GPU sharding: the shard-local
  * pass of each primitive with the cross-shard term supplied as a device scalar, so

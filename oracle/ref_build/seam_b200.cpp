@@ -4,8 +4,9 @@
  * :354-398, :530-681, :683-763, :788-975, :988-1006, :1008-1026) implemented on top of
  * libdrjit_b200.so through include/drjit_b200_thread_state.h.
  *
- * oracle/ref_build/Makefile links this file + seam_renamed.cpp in place of src/cuda_ts.cpp into
- * oracle/_ref_b200/libdrjit-core.so; the reference's own tests/reductions.cpp and tests/vcall.cpp
+ * oracle/ref_build/Makefile (`make b200`) links this file into oracle/_ref_b200/libdrjit-core.so next
+ * to the reference's unmodified cuda_ts.o whose eight primitive symbols were weakened (objcopy), so
+ * these definitions win at link time; the reference's own tests/reductions.cpp and tests/vcall.cpp
  * and tests/test_insitu_gpu.py then run through jit_block_reduce / jit_compress /
  * jit_block_mkperm(JitBackend::CUDA) of that library on the B200 box.
  *

@@ -20,13 +20,13 @@ __global__ void fill(uint8_t *m, uint64_t n, uint32_t thr) {
 
 // out must be strictly increasing, every out[j] must select a set byte, count must match popcount
 __global__ void check(const uint8_t *m, const uint32_t *out, uint64_t n, const uint32_t *count,
-                      unsigned long long *errors, unsigned long long *ones) {
+                      unsigned long long *errors, unsigned long long *ones, uint32_t base) {
     unsigned long long bad = 0, c = 0;
     const uint32_t cnt = *count;
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         c += m[i] != 0;
         if (i < cnt) {
-            bad += m[out[i]] == 0;
+            bad += (out[i] - base) >= n || m[out[i] - base] == 0;
             if (i > 0) bad += out[i] <= out[i - 1];
         }
     }
@@ -43,12 +43,13 @@ static double g_density;
 static const char *g_filter = nullptr;
 static int g_debug = 0;
 
-template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t CTAS_PER_SM = 0>
+template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t COPY = kCopyLsu, bool BASE512 = true>
 void run(uint64_t n, const char *label) {
     constexpr uint32_t TILE = kCompThreads * ROWS * kCompUnit;
+    constexpr uint32_t CTAS_PER_SM = 0;
     if (g_filter && !strstr(label, g_filter)) return;
-    auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS>;
-    constexpr uint32_t smem = STAGES * TILE;
+    auto kernel = compress_kernel<ROWS, STAGES, MIN_CTAS, COPY, BASE512>;
+    constexpr uint32_t smem = compress_smem_bytes<ROWS, STAGES, COPY>();
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kCompThreads, smem));
@@ -57,7 +58,7 @@ void run(uint64_t n, const char *label) {
     cudaFuncAttributes attr; CK(cudaFuncGetAttributes(&attr, kernel));
 
     CompressParams p{};
-    p.in = g_in; p.out = g_out; p.size = (uint32_t) n; p.index_base = 0; p.debug = (uint32_t) g_debug;
+    p.in = g_in; p.out = g_out; p.size = (uint32_t) n; p.index_base = BASE512 ? 0 : 7; p.debug = (uint32_t) g_debug;
     p.tiles = (uint32_t) ((n + TILE - 1) / TILE);
     p.state = (uint64_t *) g_scratch; p.count_out = g_count;
     const size_t state_bytes = (size_t) p.tiles * 8;
@@ -78,7 +79,7 @@ void run(uint64_t n, const char *label) {
     }
     std::sort(ts.begin(), ts.end());
     CK(cudaMemset(g_err, 0, 16));
-    if (!g_debug) check<<<g_sms * 8, 256>>>(g_in, g_out, n, g_count, g_err, g_err + 1);
+    if (!g_debug) check<<<g_sms * 8, 256>>>(g_in, g_out, n, g_count, g_err, g_err + 1, p.index_base);
     unsigned long long res[2]; CK(cudaMemcpy(res, g_err, 16, cudaMemcpyDeviceToHost));
     uint32_t cnt; CK(cudaMemcpy(&cnt, g_count, 4, cudaMemcpyDeviceToHost));
     const bool ok = res[0] == 0 && res[1] == cnt;
@@ -108,6 +109,23 @@ int main(int argc, char **argv) {
     run<4, 2, 4>(n, "ROWS=4 S=2 min4");
     run<4, 4, 3>(n, "ROWS=4 S=4 min3");
     run<8, 1, 3>(n, "ROWS=8 S=1 min3");
+    run<8, 1, 3, kCopyLsuPairs>(n, "pairs ROWS=8 S=1 min3");
+    run<8, 1, 4, kCopyLsuPairs>(n, "pairs ROWS=8 S=1 min4");
+    run<8, 2, 3, kCopyLsuPairs>(n, "pairs ROWS=8 S=2 min3");
+    run<16, 1, 2, kCopyLsuPairs>(n, "pairs ROWS=16 S=1 min2");
+    run<8, 1, 3, kCopyVec>(n, "vec ROWS=8 S=1 min3");
+    run<8, 1, 3, kCopyVec, false>(n, "vec ROWS=8 S=1 min3 base+7");
+    run<8, 1, 4, kCopyVec>(n, "vec ROWS=8 S=1 min4");
+    run<8, 2, 3, kCopyVec>(n, "vec ROWS=8 S=2 min3");
+    run<4, 2, 4, kCopyVec>(n, "vec ROWS=4 S=2 min4");
+    run<16, 1, 2, kCopyVec>(n, "vec ROWS=16 S=1 min2");
+    run<8, 1, 3, kCopyBulk>(n, "bulk ROWS=8 S=1 min3");
+    run<8, 1, 3, kCopyBulk, false>(n, "bulk ROWS=8 S=1 min3 base+7");
+    run<8, 1, 2, kCopyBulk>(n, "bulk ROWS=8 S=1 min2");
+    run<8, 2, 2, kCopyBulk>(n, "bulk ROWS=8 S=2 min2");
+    run<8, 0, 3, kCopyBulk>(n, "bulk direct ROWS=8 min3");
+    run<4, 2, 4, kCopyBulk>(n, "bulk ROWS=4 S=2 min4");
+    run<16, 1, 2, kCopyBulk>(n, "bulk ROWS=16 S=1 min2");
     run<8, 1, 4>(n, "ROWS=8 S=1 min4");
     run<8, 2, 3>(n, "ROWS=8 S=2 min3");
     run<8, 2, 2>(n, "ROWS=8 S=2 min2");

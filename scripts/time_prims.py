@@ -2,7 +2,8 @@
 """Times individual primitives with CUDA events (developer tool; not the bench contract).
 
     python scripts/time_prims.py [prim ...] [--log2 N] [--reps R]
-prims: sum block_reduce dot scan scan64 compress compress01 compress99 mkperm mkperm256 scatter all
+prims: sum block_reduce dot scan scan64 scanseg compress compress01 compress99 mkperm mkperm256 scatter sort sortkeys
+       sort_composed torch_sort (the last two only when named) all
 """
 import argparse
 import os
@@ -114,6 +115,31 @@ def main():
         bins = torch.zeros(1 << 20, dtype=torch.float32, device=dev)
         return lambda: dr.scatter_add(bins, v, i)
 
+    def s_sort(payload):
+        def setup(n):
+            k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0)
+            return (lambda: ops.sort_with_indices(k, vt=VarType.UInt32)) if payload else (lambda: ops.sort(k, vt=VarType.UInt32))
+        return setup
+
+    def s_sort_composed(n):
+        """the reference's _radix_sort structure (drjit/__init__.py:1698-1772) on this library's stable
+        block_mkperm: per pass a digit kernel, block_mkperm(256 buckets), one gather per carried array"""
+        k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0)
+
+        def fn():
+            o, idx = k, torch.arange(n, dtype=torch.int32, device=dev)
+            for shift in (0, 8, 16, 24):
+                digit = (o >> shift) & 255
+                perm, _ = ops.block_mkperm(digit, n, 256, want_offsets=False)
+                pl = perm.long()
+                o, idx = o[pl], idx[pl]
+            return o, idx
+        return fn
+
+    def s_torch_sort(n):
+        k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0)
+        return lambda: torch.sort(k, stable=True)
+
     run("sum", 28, 4, s_sum)
     run("block_reduce", 28, 4 + 4 / 256, s_br)
     run("dot", 28, 8, s_dot)
@@ -126,6 +152,12 @@ def main():
     run("mkperm", 26, 12, s_mkperm(4096))
     run("mkperm256", 26, 12, s_mkperm(256))
     run("scatter", 28, 8, s_scatter)
+    run("sort", 26, 4 * 20 + 0, s_sort(True))          # key + index: 20 B per element and pass
+    run("sortkeys", 26, 4 * 12, s_sort(False))
+    if "sort_composed" in want:
+        run("sort_composed", 26, 4 * 20, s_sort_composed)
+    if "torch_sort" in want:
+        run("torch_sort", 26, 4 * 20, s_torch_sort)
 
 
 if __name__ == "__main__":
