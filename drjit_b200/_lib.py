@@ -45,6 +45,7 @@ SIGNATURES = {
     "drjit_b200_block_prefix_reduce": (i32, [vp, i32, i32, u32, u32, i32, i32, vp, vp]),
     "drjit_b200_compress": (i32, [vp, vp, u32, vp, pu32]),
     "drjit_b200_block_mkperm": (i32, [vp, vp, u32, u32, u32, vp, vp, pu32]),
+    "drjit_b200_call_reduce": (i32, [vp, vp, u32, u32, vp, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(vp), pu32]),
     "drjit_b200_sort": (i32, [vp, i32, u32, i32, vp, vp, vp]),
     "drjit_b200_poke": (i32, [vp, vp, vp, u32]),
     "drjit_b200_aggregate": (i32, [vp, vp, vp, u32]),

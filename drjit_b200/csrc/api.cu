@@ -136,6 +136,16 @@ DRJIT_B200_API int drjit_b200_mkperm_sharded(void *stream, const uint32_t *value
     return primitive(DRJIT_B200_KT_MKPERM, size, stream, [&] { djb::mkperm_sharded(S(stream), values, size, bucket_count, index_base, perm, hist_dev); });
 }
 
+DRJIT_B200_API int drjit_b200_call_reduce(void *stream, const uint32_t *ids, uint32_t size, uint32_t bucket_count,
+                                          uint32_t *perm, uint32_t *offsets, uint32_t n_payloads,
+                                          const void *const *payload_in, void *const *payload_out,
+                                          uint32_t *unique_out) {
+    return primitive(DRJIT_B200_KT_MKPERM, size, stream, [&] {
+        const uint32_t unique = djb::call_reduce(S(stream), ids, size, bucket_count, perm, offsets, n_payloads, payload_in, payload_out);
+        if (unique_out) *unique_out = unique;
+    });
+}
+
 DRJIT_B200_API int drjit_b200_sort(void *stream, int vt, uint32_t size, int descending, const void *keys,
                                    void *keys_out, uint32_t *index_out) {
     return primitive(DRJIT_B200_KT_SORT, size, stream, [&] { djb::sort(S(stream), vt, size, descending != 0, keys, keys_out, index_out); });

@@ -398,7 +398,7 @@ compress_kernel(const CompressParams p) {
                     #pragma unroll
                     for (uint32_t j = 0; j < kCompUnit / 2; ++j) {
                         // byte j of the nibble stream = entries 2j, 2j+1 -> spread to two 16-bit fields
-                        const uint32_t xb = __byte_perm(qlo, qhi, 0x4440u | j);
+                        const uint32_t xb = __byte_perm(j < 4 ? qlo : qhi, 0u, 0x4440u | (j & 3u));   // (selector 4 = a zero byte)
                         if (2 * j < cp)
                             sts_u32(wp + 4 * j, and_or(xb * 0x1001u, 0x000f000fu, lane2));
                     }

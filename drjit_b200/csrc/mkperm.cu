@@ -29,6 +29,7 @@
 #include "tma.cuh"
 #include "runtime.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -200,10 +201,18 @@ constexpr uint32_t kBucketScanThreads = 1024;
 /// non-empty buckets then describes the GLOBAL array (start / size over all ranks, identical on
 /// every rank), rank_base[b] is where this rank's keys of bucket b begin in the global, rank-major
 /// stable order, while `totals` still receives the shard-local bucket starts the scatter pass needs.
+///
+/// sort_pow2 != 0 (jit_var_call_reduce, src/call.cpp:1346-1356: the dispatcher walks the buckets by
+/// decreasing size): the rows are collected in shared memory, bitonic-sorted by (size descending, id
+/// ascending) over sort_pow2 >= bucket_count slots and only then written to the table, so the host
+/// needs no std::sort after the wait. Dynamic shared memory: sort_pow2 * 16 bytes.
 template <bool PEER>
 __global__ void __launch_bounds__(kBucketScanThreads)
 mkperm_bucket_scan_kernel(const MkpermParams p, uint32_t *offsets, uint32_t *unique_out,
-                          uint32_t *hist_out, const PeerCtx peer, uint32_t *rank_base) {
+                          uint32_t *hist_out, const PeerCtx peer, uint32_t *rank_base, uint32_t sort_pow2) {
+    extern __shared__ __align__(16) uint64_t sort_mem[];    // [sort_pow2] keys, then [sort_pow2] rows {id, start}
+    uint64_t *sort_key = sort_mem;
+    uint2 *sort_row = reinterpret_cast<uint2 *>(sort_mem + sort_pow2);
     __shared__ uint32_t warp_sum[32], warp_uniq[32], warp_gsum[32];
     __shared__ uint32_t carry_sum, carry_uniq, carry_gsum, epoch_smem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
@@ -211,6 +220,7 @@ mkperm_bucket_scan_kernel(const MkpermParams p, uint32_t *offsets, uint32_t *uni
     uint32_t *totals = p.totals + (size_t) group * B;
 
     if (tid == 0) { carry_sum = 0; carry_uniq = 0; carry_gsum = 0; if (PEER) epoch_smem = peer_begin(peer); }
+    for (uint32_t i = tid; i < sort_pow2; i += kBucketScanThreads) sort_key[i] = ~0ull;     // padding sorts last
     __syncthreads();
     uint32_t epoch = 0;
     if constexpr (PEER) {
@@ -257,13 +267,37 @@ mkperm_bucket_scan_kernel(const MkpermParams p, uint32_t *offsets, uint32_t *uni
             totals[b] = start;
             if (PEER && rank_base) rank_base[b] = gstart + before;
             if (offsets && u) {       // quadruple layout: jit.h:2412-2419, mkperm.cuh:271-320
-                uint4 q = make_uint4(b, gstart, gn, 0u);
-                *reinterpret_cast<uint4 *>(offsets + 4 * (size_t) slot) = q;
+                if (sort_pow2) {
+                    sort_key[slot] = ((uint64_t) ~gn << 32) | slot;     // size descending, then id ascending
+                    sort_row[slot] = make_uint2(b, gstart);
+                } else {
+                    uint4 q = make_uint4(b, gstart, gn, 0u);
+                    *reinterpret_cast<uint4 *>(offsets + 4 * (size_t) slot) = q;
+                }
             }
         }
         __syncthreads();
         if (tid == 0) { carry_sum += ts_all; carry_uniq += tu_all; carry_gsum += tg_all; }
         __syncthreads();
+    }
+    if (sort_pow2 && offsets) {
+        for (uint32_t k = 2; k <= sort_pow2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < sort_pow2; i += kBucketScanThreads) {
+                    const uint32_t partner = i ^ j;
+                    if (partner > i) {
+                        const uint64_t a = sort_key[i], c = sort_key[partner];
+                        if ((a > c) == ((i & k) == 0)) { sort_key[i] = c; sort_key[partner] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = tid; i < carry_uniq; i += kBucketScanThreads) {
+            const uint64_t key = sort_key[i];
+            const uint2 row = sort_row[(uint32_t) key];
+            *reinterpret_cast<uint4 *>(offsets + 4 * (size_t) i) = make_uint4(row.x, row.y, ~(uint32_t) (key >> 32), 0u);
+        }
     }
     if (tid == 0 && offsets) {
         offsets[4 * (size_t) B] = carry_uniq;  // cuda_ts.cpp:948-951
@@ -276,13 +310,37 @@ mkperm_bucket_scan_kernel(const MkpermParams p, uint32_t *offsets, uint32_t *uni
 /// Sharded call: communicator view + optional output of this rank's start inside every global bucket
 struct MkpermPeer { PeerCtx ctx; uint32_t *rank_base; };
 
+constexpr uint32_t kMkpermMaxPayloads = 4;
+constexpr uint32_t kSortTableMaxBuckets = 8192;     // device-side sort of the bucket table (128 KiB of shared memory)
+
+/// Extras of jit_var_call_reduce (src/call.cpp:1268-1389) on top of the plain block_mkperm:
+/// the table sorted by decreasing bucket size, and 32-bit payload arrays permuted along with `perm`
+struct MkpermExtras {
+    bool sort_table = false;
+    uint32_t n_pay = 0;
+    const uint32_t *pay_in[kMkpermMaxPayloads] = {};
+    uint32_t *pay_out[kMkpermMaxPayloads] = {};
+};
+
 /// Launches the bucket scan of `p` (PEER when a communicator is given)
 static void launch_bucket_scan(cudaStream_t stream, const MkpermParams &p, uint32_t *offsets_dev, uint32_t *unique_dev,
-                               uint32_t *hist_out, const MkpermPeer *peer) {
+                               uint32_t *hist_out, const MkpermPeer *peer, bool sort_table = false) {
+    uint32_t sort_pow2 = 0, smem = 0;
+    if (sort_table && offsets_dev && p.n_groups == 1) {
+        sort_pow2 = std::max(2u, round_pow2(p.bucket_count));
+        smem = sort_pow2 * 16;
+        static std::atomic<bool> configured_on[kMaxDevices] = {};
+        std::atomic<bool> &configured = configured_on[device_props().device % kMaxDevices];
+        if (!configured.load(std::memory_order_acquire)) {
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_bucket_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kSortTableMaxBuckets * 16)));
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_bucket_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kSortTableMaxBuckets * 16)));
+            configured.store(true, std::memory_order_release);
+        }
+    }
     if (peer)
-        mkperm_bucket_scan_kernel<true><<<p.n_groups, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out, peer->ctx, peer->rank_base);
+        mkperm_bucket_scan_kernel<true><<<p.n_groups, kBucketScanThreads, smem, stream>>>(p, offsets_dev, unique_dev, hist_out, peer->ctx, peer->rank_base, sort_pow2);
     else
-        mkperm_bucket_scan_kernel<false><<<p.n_groups, kBucketScanThreads, 0, stream>>>(p, offsets_dev, unique_dev, hist_out, PeerCtx{}, nullptr);
+        mkperm_bucket_scan_kernel<false><<<p.n_groups, kBucketScanThreads, smem, stream>>>(p, offsets_dev, unique_dev, hist_out, PeerCtx{}, nullptr, sort_pow2);
     DJB_POST_LAUNCH();
 }
 
@@ -424,6 +482,11 @@ struct MkpermTileParams {
     uint32_t *rows;          // [chunks][stride] chunk totals -> exclusive chunk offsets
     const uint32_t *bucket_start; // [buckets] after the bucket scan
     uint32_t size, bucket_count, stride, tiles, tiles_per_chunk, index_base;
+    // jit_var_call_reduce: 32-bit payload arrays that travel with the permutation,
+    // pay_out[k][j] = pay_in[k][perm[j] - index_base] (the tile was just read: L2 hits)
+    uint32_t n_pay;
+    const uint32_t *pay_in[4];
+    uint32_t *pay_out[4];
     uint8_t vec;
     uint8_t debug;           // read only in -DDRJIT_B200_EXPERIMENTS builds (phases switched off for timing):
                              // 1 = copy-out without its global stores, 2 = no copy-out, 4 = no ranking, 8 = no bucket rows
@@ -478,6 +541,49 @@ __device__ __forceinline__ void tile_load_keys_packed(const MkpermTileParams &p,
             kp[k] = a | (b << 16);
         }
     }
+}
+
+/// Copy-out of a ranked tile together with the payload arrays of jit_var_call_reduce: the entry of
+/// slot j goes to perm[delta[bucket] + j] and every payload value of that key follows it to the same
+/// position. The payload tile is contiguous (tile_base ..) and was asked into L2 one tile ahead, so the
+/// reads are L2 hits in 32-byte sectors that the CTA uses up completely; four slots per thread are in
+/// flight at a time.
+template <uint32_t THREADS>
+__device__ __forceinline__ void tile_copy_out_payloads(const MkpermTileParams &p, const uint32_t *sorted, const uint32_t *delta,
+                                                       uint64_t tile_base, uint32_t n_tile, uint32_t idx0) {
+    for (uint32_t j0 = threadIdx.x; j0 < n_tile; j0 += 4 * THREADS) {
+        uint32_t at[4], local[4];
+        bool ok[4];
+        #pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            const uint32_t j = j0 + u * THREADS;
+            ok[u] = j < n_tile;
+            const uint32_t e = ok[u] ? sorted[j] : 0u;
+            at[u] = delta[e >> 16] + j; local[u] = e & 0xffffu;
+        }
+        #pragma unroll
+        for (uint32_t u = 0; u < 4; ++u)
+            if (ok[u]) p.perm[at[u]] = idx0 + local[u];
+        for (uint32_t k = 0; k < p.n_pay; ++k) {
+            const uint32_t *src = p.pay_in[k] + tile_base;
+            uint32_t *dst = p.pay_out[k];
+            uint32_t v[4];
+            #pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) v[u] = ok[u] ? __ldg(src + local[u]) : 0u;
+            #pragma unroll
+            for (uint32_t u = 0; u < 4; ++u)
+                if (ok[u]) dst[at[u]] = v[u];
+        }
+    }
+}
+
+/// Asks L2 for the payload tiles of tile `tile` (whole tiles of 16-byte aligned arrays only)
+__device__ __forceinline__ void tile_prefetch_payloads(const MkpermTileParams &p, uint64_t tile, uint32_t tile_keys) {
+    if ((tile + 1) * tile_keys > p.size)
+        return;
+    for (uint32_t k = 0; k < p.n_pay; ++k)
+        if ((((uintptr_t) p.pay_in[k]) & 15u) == 0)
+            bulk_prefetch_l2(p.pay_in[k] + tile * tile_keys, tile_keys * 4);
 }
 
 template <uint32_t THREADS, uint32_t KPT = kTileKeysPerThread>
@@ -551,7 +657,16 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
     __shared__ uint32_t warp_sum[WARPS];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
 
-    for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    // Tile order: round-robin over the CTAs (all CTAs advance through the input together, so the writes
+    // of the chip stay inside a narrow moving window per bucket). Experiments builds can switch to a
+    // blocked order (CTA c owns a contiguous range of tiles: the runs of successive tiles of a bucket
+    // are adjacent in `perm` and come from the same SM) for A/B timing: DRJIT_B200_MKPERM_DEBUG bit 16.
+    const bool blocked = DJB_DEBUG(p.debug) & 16u;
+    const uint32_t per_cta = (p.tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t tile_first = blocked ? blockIdx.x * per_cta : blockIdx.x,
+                   tile_end = blocked ? min(tile_first + per_cta, p.tiles) : p.tiles,
+                   tile_step = blocked ? 1u : gridDim.x;
+    for (uint32_t tile = tile_first; tile < tile_end; tile += tile_step) {
         const uint64_t tile_base = (uint64_t) tile * TILE;
         const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
         const bool vec = p.vec && n_tile == TILE;
@@ -564,12 +679,14 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
         // Ask L2 for everything the next tile of this CTA will read, so that its loads see an L2
         // round trip instead of DRAM latency (the kernel was latency-bound: profiles/r1d)
         if (tid == 0) {
-            const uint64_t next = (uint64_t) tile + gridDim.x;
-            if (next < p.tiles) {
+            const uint64_t next = (uint64_t) tile + tile_step;
+            if (p.n_pay && tile == tile_first) tile_prefetch_payloads(p, tile, TILE);
+            if (next < tile_end) {
                 if (p.vec && (next + 1) * TILE <= p.size)
                     bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
                 bulk_prefetch_l2(p.tile_off + next * S, S * 4);
                 bulk_prefetch_l2(p.tile_cnt + next * S, S * 2);
+                if (p.n_pay) tile_prefetch_payloads(p, next, TILE);
             }
         }
 
@@ -654,7 +771,9 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        if (!DJB_DEBUG(p.debug)) {
+        if (!DJB_DEBUG(p.debug) && p.n_pay) {
+            tile_copy_out_payloads<THREADS>(p, sorted, delta, tile_base, n_tile, idx0);
+        } else if (!DJB_DEBUG(p.debug)) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];
@@ -911,10 +1030,12 @@ mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
         }
         if (tid == 0) {
             const uint64_t next = (uint64_t) tile + gridDim.x;
+            if (p.n_pay && tile == blockIdx.x) tile_prefetch_payloads(p, tile, TILE);
             if (next < p.tiles) {
                 if (p.vec && (next + 1) * TILE <= p.size)
                     bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
                 bulk_prefetch_l2(p.tile_off + next * S, S * 4);
+                if (p.n_pay) tile_prefetch_payloads(p, next, TILE);
             }
         }
 
@@ -995,13 +1116,23 @@ mkperm_tile_scatter_stable_kernel(const MkpermTileParams p) {
 
         // ---- (4) runs of equal buckets are contiguous in `sorted` and in `perm` --------------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        #pragma unroll 4
-        for (uint32_t j = tid; j < n_tile; j += THREADS) {
-            const uint32_t e = sorted[j];
-            p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+        if (p.n_pay) {
+            tile_copy_out_payloads<THREADS>(p, sorted, delta, tile_base, n_tile, idx0);
+        } else {
+            #pragma unroll 4
+            for (uint32_t j = tid; j < n_tile; j += THREADS) {
+                const uint32_t e = sorted[j];
+                p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+            }
         }
         __syncthreads();
     }
+}
+
+/// Payload gather for the paths without a fused copy-out (small inputs, several sorting groups)
+__global__ void mkperm_gather_kernel(const uint32_t *perm, uint32_t size, uint32_t index_base, const uint32_t *in, uint32_t *out) {
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t) gridDim.x * blockDim.x)
+        out[i] = __ldg(in + (perm[i] - index_base));
 }
 
 // ---------------------------------------------------------------------------
@@ -1029,7 +1160,7 @@ static MkpermMode pick_mode(uint32_t bucket_count, uint32_t smem_budget, uint32_
 template <MkpermMode Mode>
 static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads, uint32_t smem,
                           uint32_t *offsets_dev, uint32_t *unique_dev, uint32_t *hist_out,
-                          cudaEvent_t table_ready, const MkpermPeer *peer) {
+                          cudaEvent_t table_ready, const MkpermPeer *peer, bool sort_table) {
     const uint32_t grid = p.ctas_per_group * p.n_groups;
     if (smem > 48 * 1024) {
         DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_histogram_kernel<Mode>,
@@ -1044,7 +1175,7 @@ static void launch_phases(cudaStream_t stream, MkpermParams &p, uint32_t threads
         mkperm_column_scan_kernel<<<tiles * p.n_groups, 256, 0, stream>>>(p, tiles);
         DJB_POST_LAUNCH();
     }
-    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer);
+    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer, sort_table);
     if (table_ready)
         DJB_CUDA_CHECK(cudaEventRecord(table_ready, stream)); // cuda_ts.cpp:953 (before phase 4)
     mkperm_scatter_kernel<Mode><<<grid, threads, smem, stream>>>(p);
@@ -1087,7 +1218,7 @@ static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t
 template <uint32_t THREADS, bool STABLE, uint32_t KPT = kTileKeysPerThread>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
-                             uint32_t *offsets, uint32_t *hist_out, const MkpermPeer *peer) {
+                             uint32_t *offsets, uint32_t *hist_out, const MkpermPeer *peer, const MkpermExtras &ex) {
     static_assert(!STABLE || KPT == kTileKeysPerThread, "the stable kernel has 32 keys per thread");
     constexpr uint32_t TILE = THREADS * KPT;
     const DeviceProps &dev = device_props();
@@ -1097,6 +1228,8 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     t.index_base = index_base;
     t.tiles = (uint32_t) ceil_div64(size, TILE);
     t.vec = ((uintptr_t) values % 16) == 0;
+    t.n_pay = ex.n_pay;
+    for (uint32_t k = 0; k < ex.n_pay; ++k) { t.pay_in[k] = ex.pay_in[k]; t.pay_out[k] = ex.pay_out[k]; }
 #if defined(DRJIT_B200_EXPERIMENTS)
     {
         static const int debug = env_int("DRJIT_B200_MKPERM_DEBUG", 0);
@@ -1173,7 +1306,7 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     const uint32_t col_tiles = ceil_div(bucket_count, 32);
     mkperm_column_scan_kernel<<<col_tiles, 256, 0, stream>>>(p, col_tiles);
     DJB_POST_LAUNCH();
-    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer);
+    launch_bucket_scan(stream, p, offsets_dev, unique_dev, hist_out, peer, ex.sort_table);
     cudaEvent_t ev = want_table ? thread_event() : nullptr;
     if (ev)
         DJB_CUDA_CHECK(cudaEventRecord(ev, stream));       // cuda_ts.cpp:953 (before the scatter pass)
@@ -1230,7 +1363,7 @@ static uint32_t mkperm_empty_shard(cudaStream_t stream, uint32_t bucket_count, u
 static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_t size,
                             uint32_t block_size, uint32_t bucket_count, uint32_t index_base,
                             uint32_t *perm, uint32_t *offsets, uint32_t *hist_out,
-                            const MkpermPeer *peer = nullptr) {
+                            const MkpermPeer *peer = nullptr, const MkpermExtras &ex = MkpermExtras()) {
     if (bucket_count == 0) // cuda_ts.cpp:794-795 (jitc_fail)
         raise(DRJIT_B200_EFATAL, "jit_block_mkperm(): bucket_count cannot be zero!");
     if (size == 0 && peer)
@@ -1263,9 +1396,9 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
         // a quarter of the SMs without such a tile take 16 Ki-key tiles (twice as many CTAs at work:
         // 2^18..2^21 keys 45 -> 35 us, scripts/small_sizes.py)
         if (stable && bucket_count <= 512 && size >= dev.sm_count * 24576u)
-            return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+            return mkperm_tiles<1024, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
         if (stable)                             // 16 rows + a 16 Ki-key tile (up to 1816 buckets)
-            return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+            return mkperm_tiles<512, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
         // Unordered kernel: what bounds its scatter pass is the length of a bucket's run per tile
         // (profiles/r1b_microbench.txt), so the tile is as large as shared memory allows: 48 Ki keys
         // (two 16-bit keys per register) next to the two bucket rows up to 4352 buckets, 32 Ki keys
@@ -1282,17 +1415,17 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
         const uint32_t kpt = kpt_env ? (uint32_t) kpt_env : kMkpermDefaultKpt;
 #if defined(DRJIT_B200_EXPERIMENTS)
         // (experimental, only by request: 60 Ki-key tiles with 16-bit staging entries)
-        if (kpt_env == 60 && stride * 10 + 1024 * 60 / 32 * 6 + 1024 * 60 * 2 <= dev.smem_optin - 1024 &&
+        if (kpt_env == 60 && ex.n_pay == 0 && stride * 10 + 1024 * 60 / 32 * 6 + 1024 * 60 * 2 <= dev.smem_optin - 1024 &&
             size >= dev.sm_count * 2u * 1024u * 60u)
-            return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+            return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
 #endif
         // (two co-resident 512-thread CTAs with 20 Ki / 16 Ki-key tiles were measured and are slower:
         // 0.396 / 0.499 ms against 0.348 ms, profiles/r2o_mkperm_tile_keys.txt)
         if (kpt >= 48 && fits(48))
-            return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+            return mkperm_tiles<1024, false, 48>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
         if (kpt >= 40 && fits(40))
-            return mkperm_tiles<1024, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
-        return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer);
+            return mkperm_tiles<1024, false, 40>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
+        return mkperm_tiles<1024, false>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
     }
 
     uint32_t warps = 32;
@@ -1350,14 +1483,18 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
     cudaEvent_t ev = want_table ? thread_event() : nullptr;
     switch (mode) {
         case MkpermMode::Warp:
-            launch_phases<MkpermMode::Warp>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer);
+            launch_phases<MkpermMode::Warp>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer, ex.sort_table);
             break;
         case MkpermMode::Cta:
-            launch_phases<MkpermMode::Cta>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer);
+            launch_phases<MkpermMode::Cta>(stream, p, threads, smem, offsets_dev, unique_dev, hist_out, ev, peer, ex.sort_table);
             break;
         default:
-            launch_phases<MkpermMode::Global>(stream, p, threads, 0, offsets_dev, unique_dev, hist_out, ev, peer);
+            launch_phases<MkpermMode::Global>(stream, p, threads, 0, offsets_dev, unique_dev, hist_out, ev, peer, ex.sort_table);
             break;
+    }
+    for (uint32_t k = 0; k < ex.n_pay; ++k) {       // (no fused copy-out on this path: one gather per payload)
+        mkperm_gather_kernel<<<std::min(ceil_div(size, 1024), dev.sm_count * 8), 256, 0, stream>>>(perm, size, index_base, ex.pay_in[k], ex.pay_out[k]);
+        DJB_POST_LAUNCH();
     }
 
     if (!want_table)
@@ -1370,6 +1507,34 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
 uint32_t block_mkperm(cudaStream_t stream, const uint32_t *values, uint32_t size, uint32_t block_size,
                       uint32_t bucket_count, uint32_t *perm, uint32_t *offsets) {
     return mkperm_impl(stream, values, size, block_size, bucket_count, 0, perm, offsets, nullptr);
+}
+
+/// jit_var_call_reduce (src/call.cpp:1268-1389) as one call: the permutation that groups the callable
+/// IDs, the table of non-empty buckets sorted by decreasing size (the order in which the dispatcher
+/// launches the callees, :1346-1356 -- sorted on the device, inside the bucket-scan kernel) and up to
+/// four 32-bit argument arrays permuted on the way (pay_out[k][j] = pay_in[k][perm[j]]: written
+/// where `perm` is written, which saves the separate gather pass per argument).
+uint32_t call_reduce(cudaStream_t stream, const uint32_t *ids, uint32_t size, uint32_t bucket_count,
+                     uint32_t *perm, uint32_t *offsets, uint32_t n_payloads, const void *const *pay_in,
+                     void *const *pay_out) {
+    if (n_payloads > kMkpermMaxPayloads)
+        raise(DRJIT_B200_EINVAL, "drjit_b200_call_reduce(): at most %u payload arrays (got %u)!", kMkpermMaxPayloads, n_payloads);
+    MkpermExtras ex;
+    ex.sort_table = bucket_count <= kSortTableMaxBuckets;
+    ex.n_pay = n_payloads;
+    for (uint32_t k = 0; k < n_payloads; ++k) {
+        ex.pay_in[k] = (const uint32_t *) pay_in[k]; ex.pay_out[k] = (uint32_t *) pay_out[k];
+        if (!pay_in[k] || !pay_out[k] || pay_in[k] == pay_out[k])
+            raise(DRJIT_B200_EINVAL, "drjit_b200_call_reduce(): payload arrays must be distinct non-null pointers!");
+    }
+    const uint32_t unique = mkperm_impl(stream, ids, size, std::max(size, 1u), bucket_count, 0, perm, offsets, nullptr, nullptr, ex);
+    if (offsets && size && !ex.sort_table) {
+        // more buckets than the device-side sort holds: order the rows on the host like the reference
+        struct Row { uint32_t id, start, size, unused; };
+        Row *rows = reinterpret_cast<Row *>(offsets);
+        std::stable_sort(rows, rows + unique, [](const Row &a, const Row &b) { return a.size > b.size; });
+    }
+    return unique;
 }
 
 void mkperm_sharded(cudaStream_t stream, const uint32_t *values, uint32_t size, uint32_t bucket_count,

@@ -150,6 +150,8 @@ uint32_t compress(cudaStream_t s, const uint8_t *in, uint32_t size, uint32_t ind
                   uint32_t *out, uint32_t *count_dev, bool sync);
 uint32_t block_mkperm(cudaStream_t s, const uint32_t *values, uint32_t size, uint32_t block_size,
                       uint32_t bucket_count, uint32_t *perm, uint32_t *offsets);
+uint32_t call_reduce(cudaStream_t s, const uint32_t *ids, uint32_t size, uint32_t bucket_count, uint32_t *perm,
+                     uint32_t *offsets, uint32_t n_payloads, const void *const *pay_in, void *const *pay_out);
 void mkperm_sharded(cudaStream_t s, const uint32_t *values, uint32_t size, uint32_t bucket_count,
                     uint32_t index_base, uint32_t *perm, uint32_t *hist_dev);
 void sort(cudaStream_t s, int vt, uint32_t size, bool descending, const void *keys, void *keys_out,

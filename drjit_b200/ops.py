@@ -290,6 +290,33 @@ def block_mkperm(values, block_size, bucket_count, want_offsets=True, perm=None,
     return perm, table
 
 
+def call_reduce(ids, bucket_count, payloads=()):
+    """jit_var_call_reduce (src/call.cpp:1268-1389) for evaluated callable IDs: returns
+    ``(perm, table, permuted)`` where ``table`` is a host int64 tensor (unique, 4) with rows
+    {bucket id, start, size, 0} ordered by decreasing size, and ``permuted[k] = payloads[k][perm]``
+    (32-bit element arrays, at most 4) produced by the same scatter pass."""
+    v = _check_array(ids, "ids")
+    if _vt(v) not in (VarType.UInt32, VarType.Int32):
+        raise RuntimeError("drjit_b200: call_reduce() expects 32-bit integer callable IDs")
+    n = v.numel()
+    pays = [_check_array(p, "payload") for p in payloads]
+    for p in pays:
+        if p.element_size() != 4 or p.numel() != n:
+            raise RuntimeError("drjit_b200: call_reduce(): payloads must be 32-bit arrays of the size of `ids`")
+    outs = [torch.empty_like(p) for p in pays]
+    perm = torch.empty(n, dtype=torch.int32, device=v.device)
+    offsets = _pinned_offsets(bucket_count)
+    unique = ctypes.c_uint32(0)
+    k = len(pays)
+    arr_in = (ctypes.c_void_p * builtins.max(k, 1))(*[p.data_ptr() for p in pays])
+    arr_out = (ctypes.c_void_p * builtins.max(k, 1))(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(v.device):
+        check(lib.drjit_b200_call_reduce(_stream(v), _ptr(v), n, bucket_count, _ptr(perm), _ptr(offsets), k,
+                                         arr_in, arr_out, ctypes.byref(unique)))
+    table = offsets[:4 * unique.value].clone().view(-1, 4).to(torch.int64) & 0xFFFFFFFF
+    return perm, table, outs
+
+
 # --------------------------------------------------------------------------- sort
 def _sort(value, descending, want_values, want_indices, vt=None):
     x = _check_array(value)

@@ -263,6 +263,21 @@ DRJIT_B200_API int drjit_b200_scatter_reduce(void *stream, int vt, int op, int m
                                              const uint32_t *index, const uint8_t *mask,
                                              uint32_t size);
 
+/* jit_var_call_reduce, src/call.cpp:1268-1389 (dr.dispatch / vcall reordering), as one call:
+ * block_mkperm of the callable IDs with block_size == size, plus
+ *  - the table of non-empty buckets already in the order the dispatcher uses -- decreasing bucket
+ *    size (:1346-1356; the reference std::sorts the pinned table on the host after the wait; here the
+ *    bucket-scan kernel sorts it in shared memory; ties in ascending id order), and
+ *  - up to 4 argument arrays of 32-bit elements permuted on the way: payload_out[k][j] =
+ *    payload_in[k][perm[j]] for all j, written by the scatter pass where `perm` is written (the
+ *    reference gathers every argument through `perm` in a separate pass, src/extra/call.cpp:320-452).
+ * offsets: host-pinned, 4*bucket_count+1 entries (required layout as in drjit_b200_block_mkperm).
+ * Waits for the table like drjit_b200_block_mkperm; perm / payload_out are complete in stream order. */
+DRJIT_B200_API int drjit_b200_call_reduce(void *stream, const uint32_t *ids, uint32_t size, uint32_t bucket_count,
+                                          uint32_t *perm, uint32_t *offsets, uint32_t n_payloads,
+                                          const void *const *payload_in, void *const *payload_out,
+                                          uint32_t *unique_out);
+
 /* dr.sort / dr.argsort, drjit/__init__.py:1698-1772 (`_radix_sort`: on the GPU four (eight for 64-bit
  * types) 8-bit LSD passes, each a digit kernel + jit_block_mkperm + one gather per carried array).
  * Here every pass moves the keys and the index payload itself (histogram launch + offsets launch +

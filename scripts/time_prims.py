@@ -152,6 +152,29 @@ def main():
     run("mkperm", 26, 12, s_mkperm(4096))
     run("mkperm256", 26, 12, s_mkperm(256))
     run("scatter", 28, 8, s_scatter)
+    def s_call_reduce(npay):
+        def setup(n):
+            k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0, and_=4095)
+            pays = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(npay)]
+            for i, p in enumerate(pays):
+                ops.fill_fmix32(p, 1, xor=i + 1)
+            return lambda: ops.call_reduce(k, 4096, pays)
+        return setup
+
+    def s_call_reduce_unfused(n):
+        k = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(k, 0, and_=4095)
+        pays = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+
+        def fn():
+            perm, table = ops.block_mkperm(k, n, 4096)
+            pl = perm.long()
+            return [p[pl] for p in pays]
+        return fn
+
+    if "call_reduce" in want or "all" in want:
+        run("call_reduce", 26, 12, s_call_reduce(0))
+        run("call_reduce", 26, 12 + 2 * 8, s_call_reduce(2))
+        run("call_reduce", 26, 12 + 2 * 8, s_call_reduce_unfused)
     run("sort", 26, 4 * 20 + 0, s_sort(True))          # key + index: 20 B per element and pass
     run("sortkeys", 26, 4 * 12, s_sort(False))
     if "sort_composed" in want:
