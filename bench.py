@@ -347,19 +347,28 @@ def make_prims(wl, sh, ops, ReduceOp, VarType, results):
     """The seven primitives of one step as closures (public API of drjit_b200)."""
     world = sh.world
     zero = b"\0\0\0\0"
+    import torch
+    dev = wl.x.device
+    fused = sh.comm is not None
+    # preallocated results of the fused path (a per-call torch.empty costs microseconds that show next
+    # to 20-100 us primitives at N = 8)
+    o_sum = torch.empty(1, dtype=torch.float32, device=dev); o_dot = torch.empty(1, dtype=torch.float32, device=dev)
+    o_off = torch.empty(1, dtype=torch.int32, device=dev)
+    o_hist = torch.empty(BUCKETS, dtype=torch.int32, device=dev); o_rb = torch.empty(BUCKETS, dtype=torch.int32, device=dev)
 
     def p_sum():
-        results["sum"] = sh.reduce(ReduceOp.Add, wl.x)
+        results["sum"] = sh.reduce(ReduceOp.Add, wl.x, out=o_sum) if fused else sh.reduce(ReduceOp.Add, wl.x)
 
     def p_block_reduce():
         results["br"] = sh.block_reduce(ReduceOp.Add, wl.x_br, 256, out=wl.br_out)   # block-aligned shards: no exchange
 
     def p_dot():
-        results["dot"] = sh.dot(wl.x_dot, wl.y)
+        results["dot"] = sh.dot(wl.x_dot, wl.y, out=o_dot) if fused else sh.dot(wl.x_dot, wl.y)
 
     def p_prefix():
         if world > 1:   # shard-offset form (see module docstring / DESIGN.md section 5)
-            results["scan"] = sh.prefix_reduce_offsets(ReduceOp.Add, wl.u, vt=VarType.UInt32, out=wl.u_out)
+            results["scan"] = sh.prefix_reduce_offsets(ReduceOp.Add, wl.u, vt=VarType.UInt32, out=wl.u_out,
+                                                       **({"offset": o_off} if fused else {}))
         else:
             results["scan"] = (ops.block_prefix_reduce(ReduceOp.Add, wl.u, wl.u.numel(), True, False,
                                                        vt=VarType.UInt32, out=wl.u_out), None)
@@ -369,7 +378,8 @@ def make_prims(wl, sh, ops, ReduceOp, VarType, results):
 
     def p_mkperm():
         if world > 1:
-            results["mkperm"] = sh.mkperm(wl.keys, BUCKETS, wl.range["mkperm_4096"][0] & 0xFFFFFFFF, perm=wl.perm)
+            results["mkperm"] = sh.mkperm(wl.keys, BUCKETS, wl.range["mkperm_4096"][0] & 0xFFFFFFFF, perm=wl.perm,
+                                          **({"hist": o_hist, "rank_base": o_rb, "raw_table": True} if fused else {}))
         else:           # the seam function jit_var_call_reduce calls (call.cpp:1324): pinned table + count
             results["mkperm"] = ops.block_mkperm(wl.keys, wl.keys.numel(), BUCKETS, perm=wl.perm, raw_table=True)
 
@@ -461,6 +471,8 @@ def verify(torch, dist, wl, results, rank, world, dev):
     table_exp = torch.stack([ids, gstart[ids], gsize[ids], torch.zeros_like(ids)], 1).cpu()
     if world > 1:
         perm, table = res.perm, res.table
+        if isinstance(table, tuple):        # raw pinned table + unique count (fused path)
+            table = table[0][:4 * table[1]].view(-1, 4).to(torch.int64) & M32
         good = bool(torch.equal(res.hist.long() & M32, hist_exp))
         good = good and bool(torch.equal(res.rank_base.long() & M32, (gstart + allh[:rank].sum(0)) & M32))
     else:

@@ -771,15 +771,15 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        if (!DJB_DEBUG(p.debug) && p.n_pay) {
+        if (!(DJB_DEBUG(p.debug) & 15u) && p.n_pay) {
             tile_copy_out_payloads<THREADS>(p, sorted, delta, tile_base, n_tile, idx0);
-        } else if (!DJB_DEBUG(p.debug)) {
+        } else if (!(DJB_DEBUG(p.debug) & 15u)) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];
                 p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
             }
-        } else if (DJB_DEBUG(p.debug) == 1u) {
+        } else if ((DJB_DEBUG(p.debug) & 15u) == 1u) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];

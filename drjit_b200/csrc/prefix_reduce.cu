@@ -147,6 +147,16 @@ static void launch_prefix(cudaStream_t stream, PrefixParams &p) {
     // need the array end to fall on a vector boundary.
     const bool vec = ((uintptr_t) p.in % 16) == 0 && ((uintptr_t) p.out % 16) == 0 &&
                      (!p.reverse || p.size % V == 0);
+#if defined(DRJIT_B200_EXPERIMENTS)
+    // A/B of the tile geometry for 8-byte types (scripts/time_prims.py scan64): DRJIT_B200_SCAN64_GEOM=1..3
+    if constexpr (sizeof(T) == 8) {
+        static const int geom = getenv("DRJIT_B200_SCAN64_GEOM") ? atoi(getenv("DRJIT_B200_SCAN64_GEOM")) : 0;
+        if (vec && !seg && geom == 1) return launch_prefix_geom<T, Op, false, true, 4, 3, 4>(stream, p);
+        if (vec && !seg && geom == 2) return launch_prefix_geom<T, Op, false, true, 4, 4, 3>(stream, p);
+        if (vec && !seg && geom == 3) return launch_prefix_geom<T, Op, false, true, 4, 2, 4>(stream, p);
+        if (vec && !seg && geom == 4) return launch_prefix_geom<T, Op, false, true, 4, 3, 3>(stream, p);
+    }
+#endif
     if (seg) {
         if (vec) launch_prefix_geom<T, Op, true, true, kScanRows, kScanStages, kScanCtas>(stream, p);
         else     launch_prefix_geom<T, Op, true, false, 4, 0, 1>(stream, p);

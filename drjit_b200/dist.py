@@ -22,7 +22,7 @@ import ctypes
 import torch
 import torch.distributed as dist
 
-from .ops import ReduceOp, VarType
+from .ops import ReduceOp, VarType, _on
 
 FOLD_ALL, FOLD_LOWER, FOLD_HIGHER = 0, 1, 2
 COMM_HANDLE_BYTES = 64
@@ -69,13 +69,13 @@ class PeerComm:
         self.rank, self.world, self.bulk_bytes = rank, world, bulk_bytes
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         handle = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             check(lib.drjit_b200_comm_create(rank, world, bulk_bytes, ctypes.byref(handle)))
         self.ptr = handle
 
     def handle_bytes(self):
         buf = ctypes.create_string_buffer(COMM_HANDLE_BYTES)
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             self._check(self._lib.drjit_b200_comm_handle(self.ptr, buf))
         return buf.raw
 
@@ -83,7 +83,7 @@ class PeerComm:
         """handles: the `world` window handles in rank order (bytes)"""
         blob = b"".join(handles)
         assert len(blob) == self.world * COMM_HANDLE_BYTES
-        with torch.cuda.device(self.device):
+        with _on(self.device):
             self._check(self._lib.drjit_b200_comm_connect(self.ptr, ctypes.create_string_buffer(blob, len(blob))))
         return self
 
@@ -152,14 +152,15 @@ class Sharded:
         return int(_vt(x, vt))
 
     # ------------------------------------------------------------------ reductions
-    def reduce(self, op, x, vt=None):
+    def reduce(self, op, x, vt=None, out=None):
         """dr.sum/prod/min/max over the global array. Fused path: ONE launch (shard reduction whose
         last CTA exchanges the partials over NVLink and folds them in rank order). Collective
         path: local reduce -> all-gather of W partials -> the same kernel folds them (type- and
         op-exact for unsigned types, which NCCL lacks)."""
         if self.comm is not None:
-            out = torch.empty(1, dtype=x.dtype, device=x.device)
-            with torch.cuda.device(x.device):
+            if out is None:
+                out = torch.empty(1, dtype=x.dtype, device=x.device)
+            with _on(x.device):
                 self._check(self._lib.drjit_b200_comm_reduce(self.comm.ptr, self._s(x), self._vt(x, vt), int(op),
                                                              FOLD_ALL, x.numel(), self._p(x), self._p(out)))
             return out
@@ -179,7 +180,7 @@ class Sharded:
         if self.comm is not None:
             res = ctypes.c_int(0)
             fn = self._lib.drjit_b200_comm_all if want_all else self._lib.drjit_b200_comm_any
-            with torch.cuda.device(mask.device):
+            with _on(mask.device):
                 self._check(fn(self.comm.ptr, self._s(mask), self._p(mask), mask.numel(), ctypes.byref(res)))
             return bool(res.value)
         if mask.numel() == 0:
@@ -200,10 +201,11 @@ class Sharded:
         """dr.any over the global mask."""
         return self._all_any(mask, False)
 
-    def dot(self, a, b):
+    def dot(self, a, b, out=None):
         if self.comm is not None:
-            out = torch.empty(1, dtype=a.dtype, device=a.device)
-            with torch.cuda.device(a.device):
+            if out is None:
+                out = torch.empty(1, dtype=a.dtype, device=a.device)
+            with _on(a.device):
                 self._check(self._lib.drjit_b200_comm_reduce_dot(self.comm.ptr, self._s(a), self._vt(a, None),
                                                                  self._p(a), self._p(b), a.numel(), self._p(out)))
             return out
@@ -218,7 +220,7 @@ class Sharded:
         forward scan) of every rank's 1-element device tensor ``src``. Fused path: one tiny
         peer-exchange kernel; collective path: all-gather + local fold."""
         if self.comm is not None:
-            with torch.cuda.device(src.device):
+            with _on(src.device):
                 self._check(self._lib.drjit_b200_comm_fold(self.comm.ptr, self._s(src), self._vt(src, vt), int(op),
                                                            FOLD_LOWER if lower else FOLD_ALL, self._p(src), self._p(dst)))
             return dst
@@ -237,7 +239,7 @@ class Sharded:
         if out is None:
             out = torch.empty_like(x)
         if self.comm is not None:
-            with torch.cuda.device(x.device):
+            with _on(x.device):
                 self._check(self._lib.drjit_b200_comm_prefix_reduce(
                     self.comm.ptr, self._s(x), self._vt(x, vt), int(op), x.numel(), int(exclusive), 0,
                     self._p(x), self._p(out), None, 1))
@@ -255,7 +257,7 @@ class Sharded:
     def prefix_sum(self, x, exclusive=True, vt=None, out=None):
         return self.prefix_reduce(ReduceOp.Add, x, exclusive, vt, out)
 
-    def prefix_reduce_offsets(self, op, x, exclusive=True, vt=None, out=None):
+    def prefix_reduce_offsets(self, op, x, exclusive=True, vt=None, out=None, offset=None):
         """Global prefix reduction in *shard-offset form*: returns ``(local, offset)`` where ``local``
         is the prefix reduction of this rank's shard alone and ``offset`` (1-element device tensor)
         the reduction of all lower shards, i.e. global[i] = op(offset, local[i]). This is the form
@@ -265,8 +267,9 @@ class Sharded:
         if out is None:
             out = torch.empty_like(x)
         if self.comm is not None:
-            offset = torch.empty(1, dtype=x.dtype, device=x.device)
-            with torch.cuda.device(x.device):
+            if offset is None:
+                offset = torch.empty(1, dtype=x.dtype, device=x.device)
+            with _on(x.device):
                 self._check(self._lib.drjit_b200_comm_prefix_reduce(
                     self.comm.ptr, self._s(x), self._vt(x, vt), int(op), x.numel(), int(exclusive), 0,
                     self._p(x), self._p(out), self._p(offset), 0))
@@ -291,7 +294,7 @@ class Sharded:
             if out is None:
                 out = torch.empty(mask.numel(), dtype=torch.int32, device=mask.device)
             counts = (ctypes.c_uint32 * self.world)()
-            with torch.cuda.device(mask.device):
+            with _on(mask.device):
                 self._check(self._lib.drjit_b200_comm_compress(self.comm.ptr, self._s(mask), self._p(mask),
                                                                mask.numel(), index_base & 0xFFFFFFFF, self._p(out), counts))
             return out, [int(c) for c in counts]
@@ -304,7 +307,8 @@ class Sharded:
         return out, [int(c) & 0xFFFFFFFF for c in counts.cpu().tolist()]
 
     # ------------------------------------------------------------------ mkperm
-    def mkperm(self, keys, bucket_count, index_base, perm=None, want_table=True):
+    def mkperm(self, keys, bucket_count, index_base, perm=None, want_table=True, hist=None, rank_base=None,
+               raw_table=False):
         """Shard-local permutation (entries are global indices) + the GLOBAL bucket table.
         Bucket b of the global, rank-major (= stable) order is the concatenation over ranks of
         perm_r[local_start_r[b] : local_start_r[b] + hist_r[b]], and rank r's piece begins at
@@ -316,16 +320,20 @@ class Sharded:
             from .ops import _pinned_offsets
             if perm is None:
                 perm = torch.empty(keys.numel(), dtype=torch.int32, device=dev)
-            hist = torch.empty(bucket_count, dtype=torch.int32, device=dev)
-            rank_base = torch.empty(bucket_count, dtype=torch.int32, device=dev)
+            if hist is None:
+                hist = torch.empty(bucket_count, dtype=torch.int32, device=dev)
+            if rank_base is None:
+                rank_base = torch.empty(bucket_count, dtype=torch.int32, device=dev)
             offsets = _pinned_offsets(bucket_count) if want_table else None
             unique = ctypes.c_uint32(0)
-            with torch.cuda.device(dev):
+            with _on(dev):
                 self._check(self._lib.drjit_b200_comm_mkperm(
                     self.comm.ptr, self._s(keys), self._p(keys), keys.numel(), bucket_count, index_base & 0xFFFFFFFF,
                     self._p(perm), self._p(hist), self._p(rank_base), self._p(offsets), ctypes.byref(unique)))
             table = None
-            if offsets is not None:
+            if offsets is not None and raw_table:       # the pinned buffer as the call left it (reused by the next call)
+                table = (offsets, unique.value)
+            elif offsets is not None:
                 table = offsets[:4 * unique.value].clone().view(-1, 4).to(torch.int64) & 0xFFFFFFFF
             return MkpermResult(perm, hist, rank_base, table)
         if keys.numel():
@@ -353,7 +361,7 @@ class Sharded:
         if self.world == 1:
             return bins
         if self.comm is not None and bins.numel() * bins.element_size() + 256 * self.world <= self.comm.bulk_bytes:
-            with torch.cuda.device(bins.device):
+            with _on(bins.device):
                 self._check(self._lib.drjit_b200_comm_allreduce(self.comm.ptr, self._s(bins), self._vt(bins, None),
                                                                 int(ReduceOp.Add), self._p(bins), bins.numel()))
             return bins

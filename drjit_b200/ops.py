@@ -94,8 +94,29 @@ def kernel_history_clear():
 def reserve_scratch(nbytes, device=None):
     """Pre-size the library's scratch arena of the current stream (needed before CUDA-graph capture)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib.drjit_b200_reserve_scratch(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), int(nbytes)))
+
+
+class _Noop:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOOP = _Noop()
+
+
+def _on(device):
+    """Context in which ``device`` is current: a no-op when it already is (the usual case, one
+    process per GPU) -- entering torch.cuda.device() costs a few microseconds per call, which is
+    visible next to primitives that take 20-100 us per shard."""
+    idx = device.index if isinstance(device, torch.device) else device
+    if idx is None or idx == torch.cuda.current_device():
+        return _NOOP
+    return torch.cuda.device(device)
 
 
 def _vt(x, vt=None):
@@ -130,7 +151,7 @@ def block_reduce(op, value, block_size, vt=None, out=None):
     """dr.block_reduce(op, value, block_size): reduce contiguous blocks (last one may be short)."""
     x = _check_array(value)
     n = x.numel()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         if n == 0:
             return x.new_empty(0)
         blocks = (n + block_size - 1) // block_size if block_size else 1
@@ -173,7 +194,7 @@ def _all_any(fn, mask):
     if m.dtype not in (torch.bool, torch.uint8):
         raise RuntimeError("drjit_b200: all()/any() expect a boolean mask")
     res = ctypes.c_int(0)
-    with torch.cuda.device(m.device):
+    with _on(m.device):
         check(fn(_stream(m), _ptr(m), m.numel(), ctypes.byref(res)))
     return bool(res.value)
 
@@ -194,7 +215,7 @@ def dot(a, b):
     if a.dtype != b.dtype or a.numel() != b.numel():
         raise RuntimeError("drjit_b200: dot(): incompatible operands")
     out = torch.empty(1, dtype=a.dtype, device=a.device)
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         check(lib.drjit_b200_reduce_dot(_stream(a), _vt(a), _ptr(a), _ptr(b), a.numel(), _ptr(out)))
     return out
 
@@ -208,7 +229,7 @@ def block_prefix_reduce(op, value, block_size, exclusive=True, reverse=False, vt
         out = torch.empty_like(x)
     if n == 0:
         return out
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.drjit_b200_block_prefix_reduce(_stream(x), _vt(x, vt), int(op), n, block_size,
                                                  int(exclusive), int(reverse), _ptr(x), _ptr(out)))
     return out
@@ -242,7 +263,7 @@ def compress(mask):
     idx_dtype = getattr(torch, "uint32", torch.int32)
     out = torch.empty(n, dtype=torch.int32, device=m.device)
     count = ctypes.c_uint32(0)
-    with torch.cuda.device(m.device):
+    with _on(m.device):
         check(lib.drjit_b200_compress(_stream(m), _ptr(m), n, _ptr(out), ctypes.byref(count)))
     res = out[:count.value]
     return res.view(idx_dtype) if idx_dtype is not torch.int32 else res
@@ -279,7 +300,7 @@ def block_mkperm(values, block_size, bucket_count, want_offsets=True, perm=None,
         perm = torch.empty(n, dtype=torch.int32, device=v.device)
     unique = ctypes.c_uint32(0)
     offsets = _pinned_offsets(bucket_count) if (want_offsets and block_size == n and n > 0) else None
-    with torch.cuda.device(v.device):
+    with _on(v.device):
         check(lib.drjit_b200_block_mkperm(_stream(v), _ptr(v), n, block_size, bucket_count, _ptr(perm),
                                           _ptr(offsets), ctypes.byref(unique)))
     if raw_table:
@@ -310,7 +331,7 @@ def call_reduce(ids, bucket_count, payloads=()):
     k = len(pays)
     arr_in = (ctypes.c_void_p * builtins.max(k, 1))(*[p.data_ptr() for p in pays])
     arr_out = (ctypes.c_void_p * builtins.max(k, 1))(*[o.data_ptr() for o in outs])
-    with torch.cuda.device(v.device):
+    with _on(v.device):
         check(lib.drjit_b200_call_reduce(_stream(v), _ptr(v), n, bucket_count, _ptr(perm), _ptr(offsets), k,
                                          arr_in, arr_out, ctypes.byref(unique)))
     table = offsets[:4 * unique.value].clone().view(-1, 4).to(torch.int64) & 0xFFFFFFFF
@@ -327,7 +348,7 @@ def _sort(value, descending, want_values, want_indices, vt=None):
     values = torch.empty_like(x) if want_values else None
     index = torch.empty(n, dtype=torch.int32, device=x.device) if want_indices else None
     if n:
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             check(lib.drjit_b200_sort(_stream(x), int(t), n, int(bool(descending)), _ptr(x), _ptr(values), _ptr(index)))
     return values, index
 
@@ -360,7 +381,7 @@ def scatter_reduce(op, target, value, index, active=None, mode=ReduceMode.Auto, 
         m = _check_array(active, "active")
         if m.dtype not in (torch.bool, torch.uint8) or m.numel() != val.numel():
             raise RuntimeError("drjit_b200: scatter_reduce(): invalid mask")
-    with torch.cuda.device(t.device):
+    with _on(t.device):
         check(lib.drjit_b200_scatter_reduce(_stream(t), _vt(t, vt), int(op), int(mode), _ptr(t), t.numel(),
                                             _ptr(val), _ptr(idx), _ptr(m), val.numel()))
     return target
@@ -379,7 +400,7 @@ def memset(tensor, value_bytes):
     nbytes = x.numel() * x.element_size()
     if nbytes % isize:
         raise RuntimeError("drjit_b200: memset(): size is not a multiple of the pattern")
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.drjit_b200_memset_async(_stream(x), _ptr(x), nbytes // isize, isize, buf))
     return tensor
 
@@ -387,7 +408,7 @@ def memset(tensor, value_bytes):
 def fill_fmix32(out, kind, start=0, xor=0, and_=0xFFFFFFFF):
     """Synthetic benchmark input generated on the device (tests/reductions.cpp:5-13)."""
     x = _check_array(out)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.drjit_b200_fill_fmix32(_stream(x), kind, _ptr(x), start, x.numel(), xor, and_))
     return out
 
@@ -401,7 +422,7 @@ def prefix_reduce_carry(op, value, exclusive=True, reverse=False, carry_in=None,
     x = _check_array(value)
     if out is None:
         out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.drjit_b200_prefix_reduce_carry(_stream(x), _vt(x, vt), int(op), x.numel(), int(exclusive),
                                                  int(reverse), _ptr(x), _ptr(out), _ptr(carry_in),
                                                  _ptr(total_out)))
@@ -416,7 +437,7 @@ def compress_async(mask, index_base=0, out=None, count=None):
         out = torch.empty(m.numel(), dtype=torch.int32, device=m.device)
     if count is None:
         count = torch.zeros(1, dtype=torch.int32, device=m.device)
-    with torch.cuda.device(m.device):
+    with _on(m.device):
         check(lib.drjit_b200_compress_async(_stream(m), _ptr(m), m.numel(), index_base, _ptr(out), _ptr(count)))
     return out, count
 
@@ -428,7 +449,7 @@ def mkperm_sharded(values, bucket_count, index_base=0, perm=None, hist=None):
         perm = torch.empty(v.numel(), dtype=torch.int32, device=v.device)
     if hist is None:
         hist = torch.empty(bucket_count, dtype=torch.int32, device=v.device)
-    with torch.cuda.device(v.device):
+    with _on(v.device):
         check(lib.drjit_b200_mkperm_sharded(_stream(v), _ptr(v), v.numel(), bucket_count, index_base,
                                             _ptr(perm), _ptr(hist)))
     return perm, hist
