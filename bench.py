@@ -44,7 +44,7 @@ SUITE = [
     ("block_reduce256_f32", 28, 4.0 + 4.0 / 256, "block_reduce_group_kernel<f32,Add,16 lanes>"),
     ("dot_f32", 28, 8.0, "block_reduce_chunk_kernel<f32,Add,dot>"),
     ("prefix_sum_u32", 30, 8.0, "prefix_reduce_kernel<u32,Add>"),
-    ("compress_u8", 30, 3.0, "compress_kernel<8,1,3>"),          # 1 + 4 * density, density = 0.5
+    ("compress_u8", 30, 3.0, "compress_kernel<8,1,3,kCopyLsuPairs>"),          # 1 + 4 * density, density = 0.5
     ("mkperm_4096", 26, 12.0, "mkperm_tile_hist_kernel + column/bucket scan kernels + mkperm_tile_scatter_kernel<1024,48>"),
     ("scatter_add_f32", 28, 8.0, "scatter_reduce_kernel<f32,Add>"),
 ]

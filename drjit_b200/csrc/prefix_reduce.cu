@@ -45,16 +45,27 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
         occupancy_of[dev.device % kMaxDevices].store(occupancy, std::memory_order_release);
     }
 
+    // outputs of at least twice the L2 size cannot stay resident anyway (smaller ones are left to the
+    // default policy: a consumer kernel finds them in L2)
+    p.evict_first = (uint64_t) p.size * sizeof(T) >= ((uint64_t) 256 << 20);
+#if defined(DRJIT_B200_EXPERIMENTS)
+    if (const char *env = getenv("DRJIT_B200_SCAN_EVICT_FIRST")) p.evict_first = atoi(env) != 0;    // A/B
+#endif
     p.tiles = ceil_div(p.size, Geom::TILE);
     Scratch scratch(stream);
     const size_t state_bytes = TileState<A>::bytes(p.tiles);
     p.state = scratch.device(state_bytes);
-    if (p.tiles > 1)        // (a single tile never reads a descriptor)
+    // Small arrays (wavefront loops launch these by the thousand): up to four tiles are
+    // walked by ONE CTA with the carry in registers -- no descriptor is read, so the memset launch
+    // goes away as well (one launch in total; 2^14 u32: 7.4 -> ~6 us, the reference needs 6.2).
+    p.single_cta = !SEG && p.tiles > 1 && p.tiles <= 4;
+    if (p.tiles > 1 && !p.single_cta)       // (a single tile never reads a descriptor)
         DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 
     // (the windowed carry reads one descriptor per CTA of the grid with <= kScanWindowLoads loads per thread)
-    const uint32_t grid = std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kScanWindowLoads * kScanThreads);
-    if (grid == p.tiles) {
+    const uint32_t grid = p.single_cta ? 1u
+        : std::min(std::min(p.tiles, dev.sm_count * (uint32_t) occupancy), kScanWindowLoads * kScanThreads);
+    if (grid == p.tiles || p.single_cta) {
         // One tile per CTA: a CTA only ever waits for tiles of lower-numbered CTAs, which were
         // dispatched before it, so an ordinary launch cannot deadlock (and is ~1 us cheaper)
         kernel<<<grid, threads, smem, stream>>>(p);
@@ -157,6 +168,10 @@ static void launch_prefix(cudaStream_t stream, PrefixParams &p) {
         if (vec && !seg && geom == 4) return launch_prefix_geom<T, Op, false, true, 4, 3, 3>(stream, p);
     }
 #endif
+    // Arrays of up to four tiles (32 KiB each): one CTA with direct 128-bit loads -- no TMA ring to
+    // fill, no descriptors, no memset: the latency of one launch (wavefront-sized arrays)
+    if (vec && !seg && p.size <= 4 * ScanGeom<T, true, kScanRows>::TILE)
+        return launch_prefix_geom<T, Op, false, true, kScanRows, 0, kScanCtas>(stream, p);
     if (seg) {
         if (vec) launch_prefix_geom<T, Op, true, true, kScanRows, kScanStages, kScanCtas>(stream, p);
         else     launch_prefix_geom<T, Op, true, false, 4, 0, 1>(stream, p);
