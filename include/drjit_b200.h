@@ -93,6 +93,17 @@ struct drjit_b200_aggregation_entry {
     const void *src;
 };
 
+/* CallBucket, include/drjit-core/jit.h:2470-2480 (16 bytes). jit_var_call_reduce overwrites the rows of
+ * the bucket table IN PLACE with this structure (src/call.cpp:1358-1378): a table row
+ * {id, start, size, 0} written by drjit_b200_block_mkperm / drjit_b200_call_reduce has the same size, so
+ * the pinned `offsets` buffer doubles as the CallBucket array the dispatcher returns. `index` is a
+ * tracer variable id (the sub-range of `perm`), filled in above the seam. */
+struct drjit_b200_call_bucket {
+    void *ptr;               /* resolved instance pointer (registry) */
+    uint32_t index;          /* variable holding perm[start .. start + size) */
+    uint32_t id;             /* original instance ID */
+};
+
 /* ---- library / device management ---------------------------------------- */
 
 /* Thread-local text of the last error raised on the calling thread ("" if none). */

@@ -152,6 +152,33 @@ def main():
     L.ref_free(off_ptr)
     del keys, perm_r, canon_r, canon_o, k64, pr, po
 
+    # ---- dr.argsort of 2^26 u32: the reference's _radix_sort (drjit/__init__.py:1698-1772) --------------
+    # 4 x (digit kernel, jit_block_mkperm(256 buckets) of the reference's CUDA backend, one gather per
+    # carried array); the digit extraction and the gathers are JIT kernels in the reference, torch
+    # elementwise / index kernels stand in for them here (same memory traffic).
+    n = 1 << (26 - S)
+    keys = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(keys, 0)
+    perm_r = torch.empty_like(keys)
+    res = {}
+
+    def ref_sort():
+        o, idx = keys, torch.arange(n, dtype=torch.int32, device=dev)
+        for shift in (0, 8, 16, 24):
+            digit = ((o >> shift) & 255).contiguous()
+            torch.cuda.synchronize()
+            L.ref_block_mkperm(ref.CUDA, vp(digit.data_ptr()), n, n, 256, vp(perm_r.data_ptr()), None)
+            L.ref_sync()
+            pl = perm_r.long()
+            o, idx = o[pl], idx[pl]
+        res["r"] = (o, idx)
+
+    t_ref = time_ref(L, ref_sort)
+    t_ours = time_ours(lambda: res.__setitem__("o", ops.sort_with_indices(keys, vt=VarType.UInt32)))
+    torch.cuda.synchronize()
+    ok = torch.equal(res["r"][0], res["o"][0]) and torch.equal(res["r"][1], res["o"][1])
+    report("argsort u32 (keys + index)", n, 80, t_ref, t_ours, "sorted keys and permutation " + ("bit-exact" if ok else "MISMATCH"))
+    del keys, perm_r, res
+
     # ---- scatter-add histogram -------------------------------------------------------------------------
     n = 1 << (28 - S); bins = 1 << max(4, 20 - S)
     val = torch.empty(n, dtype=torch.float32, device=dev); ops.fill_fmix32(val, 1)

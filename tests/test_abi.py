@@ -116,6 +116,7 @@ int main() {
     if (ts.compress((const uint8_t *) buf, 0, buf) != 0) return 7;
     if (ts.block_mkperm(buf, 0, 1, 4, buf, nullptr) != 0) return 8;
     static_assert(sizeof(AggregationEntry) == 16, "layout");
+    static_assert(sizeof(drjit_b200_call_bucket) == 16, "a table row is overwritten in place by a CallBucket");
     return 0;
 }
 ''')
