@@ -50,6 +50,9 @@ def lib(cuda=False, llvm=True):
         if hasattr(L, "ref_kernel_history"):
             L.ref_set_flag.argtypes = [u32, i32]
             L.ref_kernel_history.argtypes = [vp, vp, vp, vp, u32]; L.ref_kernel_history.restype = u32
+        if hasattr(L, "ref_scatter_reduce_masked"):
+            L.ref_scatter_reduce_masked.argtypes = [i32, i32, i32, i32, vp, u32, vp, vp, vp, u32]
+            L.ref_kernel_history_ir_count.argtypes = [ctypes.c_char_p]; L.ref_kernel_history_ir_count.restype = u32
         _lib = L
     want = (2 if cuda else 0) | (4 if llvm else 0)
     if want & ~_backends:

@@ -141,3 +141,38 @@ SHIM uint32_t ref_kernel_history(uint32_t *backends, uint32_t *types, uint32_t *
     return n;
 }
 SHIM void ref_kernel_history_clear() { jit_kernel_history_clear(); }
+
+/// dr.scatter_reduce through the reference tracer with an explicit mask array (u8 device array, one
+/// entry per element, may be NULL) -- otherwise like ref_scatter_reduce.
+SHIM int ref_scatter_reduce_masked(int backend, int vt, int op, int mode, void *target, uint32_t target_size,
+                                   void *value, void *index, void *mask, uint32_t size) {
+    return guard([&] {
+        JitBackend be = (JitBackend) backend;
+        uint32_t vt_ = jit_var_mem_map(be, (VarType) vt, target, target_size, 0),
+                 vv  = jit_var_mem_map(be, (VarType) vt, value, size, 0),
+                 vi  = jit_var_mem_map(be, VarType::UInt32, index, size, 0),
+                 vm  = mask ? jit_var_mem_map(be, VarType::Bool, mask, size, 0) : jit_var_bool(be, true);
+        uint32_t vr = jit_var_scatter(vt_, vv, vi, vm, (ReduceOp) op, (ReduceMode) mode);
+        jit_var_eval(vr);
+        void *p = nullptr;
+        jit_var_data(vr, &p);
+        if (p != target)
+            jit_memcpy_async(be, target, p, (size_t) target_size * (vt == (int) VarType::Float64 || vt == (int) VarType::UInt64 || vt == (int) VarType::Int64 ? 8 : 4));
+        jit_var_dec_ref(vr); jit_var_dec_ref(vv); jit_var_dec_ref(vi); jit_var_dec_ref(vm);
+    });
+}
+
+/// Number of kernel-history entries whose IR (the PTX the JIT generated) contains `needle`;
+/// consumes the history like ref_kernel_history.
+SHIM uint32_t ref_kernel_history_ir_count(const char *needle) {
+    KernelHistoryEntry *data = jit_kernel_history();
+    uint32_t n = 0;
+    if (!data)
+        return 0;
+    for (KernelHistoryEntry *e = data; (uint32_t) e->backend; ++e) {
+        if (e->ir && strstr(e->ir, needle)) ++n;
+        free(e->ir);
+    }
+    free(data);
+    return n;
+}

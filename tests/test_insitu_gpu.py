@@ -8,7 +8,11 @@ is the unmodified reference). On the GPU box
    aggregate parameter blocks) run their CUDA cases through the new kernels, and
  * jit_block_reduce / jit_block_prefix_reduce / jit_compress / jit_block_mkperm(JitBackend::CUDA) of
    that library are checked against the C oracle, with JitFlag::KernelHistory entries carrying the
-   reference's KernelType tags and JitFlag::LaunchBlocking honoured (cuda_ts.cpp:19-46).
+   reference's KernelType tags and JitFlag::LaunchBlocking honoured (cuda_ts.cpp:19-46), and
+ * dr.scatter_reduce traced by the reference's JIT with the B200 scatter template linked in
+   (oracle/ref_build/seam_scatter_b200.cpp, SURVEY section 8 row f3: match.any + redux.sync for
+   ReduceMode::Local on 32-bit integers; tests/mem.cpp covers the forwarded float paths) matches the
+   oracle for every (type, op) pair, masked and unmasked, and the generated PTX contains redux.sync.
 
 The second half runs in a subprocess: the patched and the unmodified libdrjit-core.so cannot share
 one process (same symbols)."""
@@ -31,7 +35,7 @@ def _need(path):
     return path
 
 
-@pytest.mark.parametrize("name", ["reductions", "vcall"])
+@pytest.mark.parametrize("name", ["reductions", "vcall", "mem"])
 def test_reference_test_program_through_b200_kernels(name, tmp_path):
     exe = _need(os.path.join(B200, f"test_{name}"))
     (tmp_path / f"out_{name}").mkdir()          # the harness writes its logs to out_<name>/ of the cwd
@@ -152,6 +156,89 @@ assert got == int(u.sum(dtype=np.uint32)), "LaunchBlocking: result not ready on 
 L.ref_set_flag(LB, 0)
 print("insitu ok:", cnt, "history entries,", len(expect_types), "primitive calls")
 """
+
+
+SCATTER_BODY = r"""
+import ctypes
+import numpy as np
+from oracle import capi, ref
+from oracle.capi import OP, VT
+
+assert ref.REF_DIR.endswith("_ref_b200")
+L = ref.lib(cuda=True, llvm=False)
+assert ref.has_backend(ref.CUDA)
+vp = ctypes.c_void_p
+CUDA = ref.CUDA
+KH = 1 << 15
+LOCAL, DIRECT = 2, 1
+
+def dev(a):
+    p = L.ref_malloc(CUDA, max(a.nbytes, 4), 0)
+    L.ref_memcpy(CUDA, vp(p), a.ctypes.data_as(vp), a.nbytes)
+    return p
+
+def host(p, n, dt):
+    a = np.empty(n, dt)
+    L.ref_sync()
+    L.ref_memcpy(CUDA, a.ctypes.data_as(vp), vp(p), a.nbytes)
+    return a
+
+n = 100_003
+checked = 0
+for bins, pattern in ((1, "one counter"), (7, "few bins"), (1 << 12, "histogram")):
+    idx = (capi.fmix32(n, xor=0x85EBCA6B) % np.uint32(bins)).astype(np.uint32)
+    mask = (capi.fmix32(n, xor=3) & 3 != 0).astype(np.uint8)          # 75 % active
+    d_idx, d_mask = dev(idx), dev(mask)
+    for vt, dt in (("u32", np.uint32), ("i32", np.int32)):
+        raw = capi.fmix32(n, xor=11)
+        val = (raw & 0xFFFF).astype(np.uint32).view(dt) if vt == "u32" else ((raw & 0xFFFF).astype(np.int64) - 0x8000).astype(np.int32)
+        d_val = dev(val)
+        for op in ("add", "min", "max", "and", "or"):
+            for use_mask in (False, True):
+                init = {"add": 5, "min": 0x7fff0000 if vt == "i32" else 0xffff0000, "max": -0x7fff0000 if vt == "i32" else 0,
+                        "and": -1 if vt == "i32" else 0xffffffff, "or": 0}[op]
+                target = np.full(bins, init, dtype=np.int64).astype(dt)
+                exp = capi.scatter_reduce(vt, op, target, val, idx, mask if use_mask else None)
+                d_t = dev(target)
+                L.ref_set_flag(KH, 1)
+                rv = L.ref_scatter_reduce_masked(CUDA, VT[vt], OP[op], LOCAL, vp(d_t), bins, vp(d_val), vp(d_idx),
+                                                 vp(d_mask) if use_mask else None, n)
+                assert rv == 0, L.ref_last_error()
+                got = host(d_t, bins, dt)
+                assert np.array_equal(got, exp), (pattern, vt, op, use_mask)
+                # the JIT kernel of this call was generated by the B200 template
+                assert L.ref_kernel_history_ir_count(b"redux.sync") >= 1, (pattern, vt, op, use_mask)
+                L.ref_set_flag(KH, 0)
+                L.ref_free(vp(d_t))
+                checked += 1
+        L.ref_free(vp(d_val))
+    # forwarded paths stay the reference's: f32 add in Local and Direct mode, u32 add in Direct mode
+    f = capi.unit_f32(n); d_f = dev(f)
+    for mode in (LOCAL, DIRECT):
+        d_t = dev(np.zeros(bins, np.float32))
+        L.ref_set_flag(KH, 1)
+        assert L.ref_scatter_reduce_masked(CUDA, VT["f32"], OP["add"], mode, vp(d_t), bins, vp(d_f), vp(d_idx), None, n) == 0
+        got = host(d_t, bins, np.float32)
+        exp = capi.scatter_reduce("f32", "add", np.zeros(bins, np.float32), f, idx, acc64=True)
+        assert np.all(np.abs(got - exp) <= 1e-4 * np.maximum(np.abs(exp), 1)), (pattern, mode)
+        assert L.ref_kernel_history_ir_count(b"redux.sync") == 0
+        L.ref_set_flag(KH, 0)
+        L.ref_free(vp(d_t))
+    L.ref_free(vp(d_f)); L.ref_free(vp(d_idx)); L.ref_free(vp(d_mask))
+print("scatter template ok:", checked, "integer cases")
+"""
+
+
+def _run_body(body, marker):
+    _need(os.path.join(B200, "libref_shim.so"))
+    env = dict(os.environ, ORACLE_REF_DIR=B200, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, "-c", body], cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert marker in out.stdout
+
+
+def test_jit_scatter_template_redux_path_vs_oracle():
+    _run_body(SCATTER_BODY, "scatter template ok")
 
 
 def test_jit_entry_points_of_patched_library_vs_oracle():
