@@ -5,18 +5,26 @@
  * kernels: ReduceMode::Local on 32-bit integers.
  *
  * The reference finds the lanes of a warp that hit the same address with match.any and then reduces
- * their values with five shuffle + op steps when the whole warp agrees, or with a data-dependent
- * loop of shuffles, ballots and bit tricks when it does not (10 ... ~60 instructions). From sm_80 on
- * the hardware does exactly this reduction in ONE instruction for 32-bit integers:
+ * their values with five shuffle + op steps -- but only when ALL 32 lanes are active and agree
+ * (`peers == -1`); a warp with masked-off lanes or a tail warp takes the general path, a
+ * data-dependent loop of shuffles, ballots and bit tricks (~14 instructions per round, 5 rounds for
+ * a warp-wide group), even when every active lane targets the same counter. That case -- counters,
+ * loss accumulators, `scatter_reduce(op, target, value, 0, active)` -- is what this template makes
+ * cheap: when all ACTIVE lanes agree, sm_80+ hardware does the whole reduction in one instruction:
  *
- *     match.any.sync.b32  peers, key, active        // lanes with my address
- *     redux.sync.<op>.<t> acc, value, peers         // reduction over that group (disjoint groups of
- *                                                   // one warp execute it side by side)
- *     @leader red.global.<op>.<t> [addr], acc       // lowest lane of the group: one atomic
+ *     match.all.sync.b32  peers|coherent, key, active   // do all active lanes hit one address?
+ *     redux.sync.<op>.<t> acc, value, active            // one instruction, any set of active lanes
+ *     @leader red.global.<op>.<t> [addr], acc           // lowest active lane: one atomic
  *
- * for op in {add, min, max, and, or}, t in {s32, u32, b32}. Everything else -- floats, 64-bit types,
- * Direct / NoConflicts modes, f16 pairs, the packet path of cuda_packet.cpp -- is forwarded to the
- * reference's own generator.
+ * for op in {add, min, max, and, or}, t in {s32, u32, b32}. Warps whose lanes disagree fall through
+ * to the reference's own generator, which is emitted behind the fast path. Two things measured on
+ * the B200 shaped this (profiles/r4j_scatter_template_ab*.txt): redux.sync with k disjoint group
+ * masks costs ~25 cycles per mask, so it only pays for ONE group (a first version that used it for
+ * every group was 2.4x slower at 2^20 random bins); and match.any is the bottleneck of the Local mode
+ * on this chip (~64 cycles per warp: 107 G elements/s at 2^20 bins against 189 G/s for plain REDs),
+ * so the coherence test must not be a second match.any -- match.all is a single cheap vote. Everything else -- floats, 64-bit types, Direct /
+ * NoConflicts modes, f16 pairs, the packet path of cuda_packet.cpp -- goes to the reference's
+ * generator unchanged.
  *
  * Integration (oracle/ref_build/Makefile, `make b200`): the unmodified cuda_scatter.o is linked twice,
  * once with jitc_cuda_render_scatter_reduce weakened (so this definition wins for every caller) and
@@ -57,8 +65,9 @@ void jitc_cuda_render_scatter_reduce(const Variable *v, const Variable *ptr, con
     }
 
     const bool is_unmasked = mask->is_literal() && mask->literal == 1;
+    const uint32_t uid = v->reg_index;
     if (!is_unmasked)
-        fmt("    @!$v bra l_$u_b200_done;\n", mask, v->reg_index);
+        fmt("    @!$v bra l_$u_b200_done;\n", mask, uid);
 
     jitc_cuda_prepare_index(ptr, index, value);      // address of the target element -> %rd3
 
@@ -74,19 +83,26 @@ void jitc_cuda_render_scatter_reduce(const Variable *v, const Variable *ptr, con
     fmt("    {\n"
         "        .reg .b32 %b2_active, %b2_key, %b2_peers, %b2_below, %b2_acc;\n"
         "        .reg .b64 %b2_word;\n"
-        "        .reg .pred %b2_leader;\n"
+        "        .reg .pred %b2_leader, %b2_coherent;\n"
         "        activemask.b32 %b2_active;\n"
         "        shr.b64 %b2_word, %rd3, 2;\n"
         "        cvt.u32.u64 %b2_key, %b2_word;\n"
-        "        match.any.sync.b32 %b2_peers, %b2_key, %b2_active;\n"
-        "        redux.sync.$s.$s %b2_acc, $v, %b2_peers;\n"
+        "        match.all.sync.b32 %b2_peers|%b2_coherent, %b2_key, %b2_active;\n"
+        "        @!%b2_coherent bra l_$u_b200_general;\n"
+        "        redux.sync.$s.$s %b2_acc, $v, %b2_active;\n"
         "        mov.u32 %b2_below, %lanemask_lt;\n"
-        "        and.b32 %b2_below, %b2_below, %b2_peers;\n"
+        "        and.b32 %b2_below, %b2_below, %b2_active;\n"
         "        setp.eq.u32 %b2_leader, %b2_below, 0;\n"
         "        @%b2_leader red.global.$s.$s [%rd3], %b2_acc;\n"
-        "    }\n",
-        name, type, value, name, type);
+        "        bra l_$u_b200_done2;\n"
+        "    }\n"
+        "l_$u_b200_general:\n",
+        uid, name, type, value, name, type, uid, uid);
 
+    // lanes of this warp disagree: the reference's generator (its own mask test is a no-op here)
+    ref_jitc_cuda_render_scatter_reduce(v, ptr, value, index, mask);
+
+    fmt("l_$u_b200_done2:\n", uid);
     if (!is_unmasked)
-        fmt("\nl_$u_b200_done:\n", v->reg_index);
+        fmt("\nl_$u_b200_done:\n", uid);
 }

@@ -25,22 +25,24 @@ n = 1 << 26
 def dev(a):
     p = L.ref_malloc(CUDA, a.nbytes, 0); L.ref_memcpy(CUDA, vp(p), a.ctypes.data_as(vp), a.nbytes); return p
 val = (capi.fmix32(n, xor=11) & 0xFFFF).astype(np.uint32); d_val = dev(val)
+mask = (capi.fmix32(n, xor=3) & 3 != 0).astype(np.uint8); d_mask = dev(mask)          # 75 % active
 N = 64
 b = (ctypes.c_uint32 * N)(); t = (ctypes.c_uint32 * N)(); s = (ctypes.c_uint32 * N)(); ms = (ctypes.c_float * N)()
 for bins in (1, 64, 1 << 12, 1 << 20):
     idx = (capi.fmix32(n, xor=0x85EBCA6B) % np.uint32(bins)).astype(np.uint32); d_idx = dev(idx)
-    for op in ("add", "max"):
+    for op, masked in (("add", False), ("add", True), ("max", True)):
         d_t = dev(np.zeros(bins, np.uint32))
         best = 1e9
         for rep in range(4):
             L.ref_set_flag(1 << 15, 1)
-            assert L.ref_scatter_reduce(CUDA, VT["u32"], OP[op], LOCAL, vp(d_t), bins, vp(d_val), vp(d_idx), n) == 0
+            assert L.ref_scatter_reduce_masked(CUDA, VT["u32"], OP[op], LOCAL, vp(d_t), bins, vp(d_val), vp(d_idx),
+                                               vp(d_mask) if masked else None, n) == 0
             L.ref_sync()
             cnt = L.ref_kernel_history(b, t, s, ms, N)
             jit = [ms[i] for i in range(cnt) if t[i] == 0 and s[i] == n]
             L.ref_set_flag(1 << 15, 0)
             if rep and jit: best = min(best, jit[-1])
-        print(f"{sys.argv[1]:10s} u32 {op:3s} 2^26 values -> {bins:8d} bins  {best:8.3f} ms  {n / best / 1e6:8.1f} Gelem/s", flush=True)
+        print(f"{sys.argv[1]:10s} u32 {op:3s} {'masked 75%' if masked else 'unmasked  '} 2^26 values -> {bins:8d} bins  {best:8.3f} ms  {n / best / 1e6:8.1f} Gelem/s", flush=True)
         L.ref_free(vp(d_t))
     L.ref_free(vp(d_idx))
 """
