@@ -24,6 +24,8 @@
  *            (same contract as the reference's "small" variant, jit.h:2404-2406).
  *   GLOBAL : global-memory atomics for bucket counts beyond shared memory ("large").
  */
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "comm.cuh"
 #include "tma.cuh"
@@ -793,6 +795,198 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
 #if defined(DRJIT_B200_EXPERIMENTS)
 // ---------------------------------------------------------------------------
+//  Unordered tile scatter, two tiles per cluster of two CTAs (runs merged through distributed shared memory)
+// ---------------------------------------------------------------------------
+//  What bounds the kernel above is the store path of its copy-out: a bucket's run is ~12 entries per
+//  48 Ki-key tile at 4096 buckets, i.e. partial, unaligned lines towards L2. Here two CTAs on two SMs
+//  (a thread-block cluster) rank two CONSECUTIVE tiles; the runs of a bucket in consecutive tiles are
+//  adjacent in `perm`, so after a cluster barrier CTA r copies out the buckets of its half of the
+//  bucket range for BOTH tiles -- its own staged entries from local shared memory, the other tile's
+//  through distributed shared memory -- one warp per bucket at a time: lanes [0, cA) write tile A's
+//  run, lanes [cA, cA + cB) tile B's, one store instruction covers both (runs of ~24 entries).
+//  Measured in isolation (scripts/microbench_cluster.cu): 0.129 ms for the stores of 2^26 entries
+//  instead of 0.228 ms. Phases (1) and (2) are those of the kernel above.
+//  RESULT (profiles/r4k_*): correct (parity tests + racecheck) but SLOWER -- 0.56-0.62 ms against 0.35 ms
+//  for the whole mkperm. The isolated measurement mapped merged slots to buckets with pure arithmetic
+//  (uniform runs); real runs vary, and finding "which bucket, which tile" per store costs ~45
+//  instructions and a remote shared-memory round trip per bucket where the single-tile copy-out
+//  spends 6 instructions per 32 entries. EXPERIMENTS builds only (DRJIT_B200_MKPERM_PAIR=1).
+template <uint32_t THREADS, uint32_t KPT>
+__global__ void __launch_bounds__(THREADS, 1)
+mkperm_tile_scatter_pair_kernel(const MkpermTileParams p) {
+    namespace cg = cooperative_groups;
+    constexpr uint32_t TILE = THREADS * KPT, WARPS = THREADS / 32;
+    constexpr bool PACKED = KPT > kTileKeysPerThread;
+    static_assert(TILE <= 65536, "local indices and run descriptors are packed into 16 bits");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t S = p.stride;
+    uint32_t *cursor = smem;             // [S] next free slot of the bucket -> (after ranking) end of its run
+    uint32_t *delta = smem + S;          // [S] final position of the bucket's run minus its local start
+    uint32_t *sorted = smem + 2 * S;     // [TILE] (bucket << 16 | local index), ordered by bucket
+    __shared__ uint32_t warp_sum[WARPS];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();                     // 0: even tile of the pair, 1: odd tile
+    const uint32_t pairs = (p.tiles + 1) / 2, pair_step = gridDim.x / 2;
+    const uint32_t *tile_smem[2] = { rank == 0 ? smem : cluster.map_shared_rank(smem, 0),
+                                     rank == 1 ? smem : cluster.map_shared_rank(smem, 1) };
+    // my half of the buckets (split at a multiple of 32: a warp takes 32 buckets per round)
+    const uint32_t split = min(S, ((S / 2 + 31) / 32) * 32), h0 = rank ? split : 0u, h1 = rank ? S : split;
+
+    for (uint32_t pair = blockIdx.x / 2; pair < pairs; pair += pair_step) {
+        const uint32_t tile = 2 * pair + rank;
+        const bool present = tile < p.tiles;                        // (an odd tile count leaves the last pair half empty)
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t n_tile = present ? (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base) : 0u;
+        const bool vec = p.vec && n_tile == TILE;
+
+        if (present) {
+            uint32_t key[PACKED ? KPT / 2 : KPT];
+            if constexpr (PACKED)
+                tile_load_keys_packed<THREADS, KPT>(p, tile_base, n_tile, key);
+            else
+                tile_load_keys<THREADS>(p, tile_base, n_tile, key);
+            if (tid == 0) {
+                const uint64_t next = (uint64_t) tile + 2ull * pair_step;
+                if (next < p.tiles) {
+                    if (p.vec && (next + 1) * TILE <= p.size)
+                        bulk_prefetch_l2(p.values + next * TILE, TILE * 4);
+                    bulk_prefetch_l2(p.tile_off + next * S, S * 4);
+                    bulk_prefetch_l2(p.tile_cnt + next * S, S * 2);
+                }
+            }
+            // ---- (1) bins: thread t owns 8 consecutive buckets per round ----------------------
+            {
+                const uint32_t chunk = tile / p.tiles_per_chunk;
+                const uint16_t *cnt = p.tile_cnt + (size_t) tile * S;
+                const uint32_t *toff = p.tile_off + (size_t) tile * S, *crow = p.rows + (size_t) chunk * S;
+                uint32_t carry = 0;
+                for (uint32_t base = 0; base < S; base += THREADS * 8) {
+                    const uint32_t b0 = base + tid * 8;
+                    uint32_t c[8], g[8];
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) { c[j] = 0; g[j] = 0; }
+                    if (b0 < S) {
+                        const uint4 cc = __ldg(reinterpret_cast<const uint4 *>(cnt + b0));
+                        const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(toff + b0)),
+                                    t1 = __ldg(reinterpret_cast<const uint4 *>(toff + b0 + 4)),
+                                    r0 = __ldg(reinterpret_cast<const uint4 *>(crow + b0)),
+                                    r1 = __ldg(reinterpret_cast<const uint4 *>(crow + b0 + 4));
+                        uint32_t s8[8];
+                        #pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) s8[j] = b0 + j < p.bucket_count ? __ldg(p.bucket_start + b0 + j) : 0u;
+                        c[0] = cc.x & 0xffffu; c[1] = cc.x >> 16; c[2] = cc.y & 0xffffu; c[3] = cc.y >> 16;
+                        c[4] = cc.z & 0xffffu; c[5] = cc.z >> 16; c[6] = cc.w & 0xffffu; c[7] = cc.w >> 16;
+                        g[0] = t0.x + r0.x + s8[0]; g[1] = t0.y + r0.y + s8[1]; g[2] = t0.z + r0.z + s8[2]; g[3] = t0.w + r0.w + s8[3];
+                        g[4] = t1.x + r1.x + s8[4]; g[5] = t1.y + r1.y + s8[5]; g[6] = t1.z + r1.z + s8[6]; g[7] = t1.w + r1.w + s8[7];
+                    }
+                    uint32_t sum = 0;
+                    #pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) sum += c[j];
+                    uint32_t incl = sum;
+                    #pragma unroll
+                    for (uint32_t d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = shfl_up(incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    if (lane == 31) warp_sum[warp] = incl;
+                    __syncthreads();
+                    uint32_t wbase = 0, total = 0;
+                    #pragma unroll
+                    for (uint32_t w = 0; w < WARPS; ++w) {
+                        if (w == warp) wbase = total;
+                        total += warp_sum[w];
+                    }
+                    uint32_t run = carry + wbase + incl - sum;
+                    carry += total;
+                    if (b0 < S) {
+                        uint32_t st[8];
+                        #pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) { st[j] = run; g[j] -= run; run += c[j]; }
+                        *reinterpret_cast<uint4 *>(cursor + b0) = make_uint4(st[0], st[1], st[2], st[3]);
+                        *reinterpret_cast<uint4 *>(cursor + b0 + 4) = make_uint4(st[4], st[5], st[6], st[7]);
+                        *reinterpret_cast<uint4 *>(delta + b0) = make_uint4(g[0], g[1], g[2], g[3]);
+                        *reinterpret_cast<uint4 *>(delta + b0 + 4) = make_uint4(g[4], g[5], g[6], g[7]);
+                    }
+                    __syncthreads();
+                }
+            }
+            // ---- (2) keys: slot from the bucket's cursor, entry stored at the slot ---------------
+            #pragma unroll
+            for (uint32_t k = 0; k < KPT; ++k) {
+                const uint32_t local = vec ? ((k / 4) * THREADS + tid) * 4 + (k & 3u) : k * THREADS + tid;
+                if constexpr (PACKED) {
+                    const uint32_t b = (key[k >> 1] >> (16 * (k & 1u))) & 0xffffu;
+                    if (b != 0xffffu)
+                        sorted[atomicAdd(cursor + b, 1u)] = (b << 16) | local;
+                } else {
+                    if (key[k] != 0xffffffffu)
+                        sorted[atomicAdd(cursor + key[k], 1u)] = (key[k] << 16) | local;
+                }
+            }
+        } else {
+            for (uint32_t b = tid; b < S; b += THREADS) cursor[b] = 0;       // empty tile: every run ends at 0
+        }
+        cluster.sync();             // both tiles are ranked; their shared memory is readable cluster-wide
+
+        // ---- (3) my half of the buckets, both tiles: one warp per bucket, 32 buckets per round -----
+        const uint32_t idx0[2] = { p.index_base + (uint32_t) ((uint64_t) (2 * pair) * TILE),
+                                   p.index_base + (uint32_t) ((uint64_t) (2 * pair + 1) * TILE) };
+        for (uint32_t cb = h0 + warp * 32; cb < h1; cb += WARPS * 32) {
+            const uint32_t b = cb + lane;
+            const bool valid = b < h1;
+            // run descriptors of bucket b in both tiles: start | count << 16, and the delta
+            uint32_t desc[2], dl[2];
+            #pragma unroll
+            for (uint32_t q = 0; q < 2; ++q) {
+                const uint32_t *cur_q = tile_smem[q], *delta_q = tile_smem[q] + S;
+                const uint32_t end = valid ? cur_q[b] : 0u;
+                uint32_t start = shfl_up(end, 1);
+                if (lane == 0) start = cb ? cur_q[cb - 1] : 0u;
+                desc[q] = valid ? (start | ((end - start) << 16)) : 0u;
+                dl[q] = valid ? delta_q[b] : 0u;
+            }
+            const uint32_t nb = min(32u, h1 - cb);
+            // four buckets per step: the (remote) loads of all four are in flight before the first store
+            for (uint32_t k0 = 0; k0 < nb; k0 += 4) {
+                uint32_t e[4], at[4], tot[4], cAs[4], sAs[4], gAs[4], sBs[4], gBs[4];
+                #pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    const uint32_t k = min(k0 + u, 31u);
+                    const uint32_t dA = k0 + u < nb ? shfl_idx(desc[0], k) : 0u, dB = k0 + u < nb ? shfl_idx(desc[1], k) : 0u;
+                    const uint32_t sA = dA & 0xffffu, cA = dA >> 16, sB = dB & 0xffffu, cB = dB >> 16;
+                    const uint32_t gA = shfl_idx(dl[0], k) + sA, gB = shfl_idx(dl[1], k) + sB;
+                    tot[u] = cA + cB; cAs[u] = cA; sAs[u] = sA; gAs[u] = gA; sBs[u] = sB; gBs[u] = gB;
+                    const bool second = lane >= cA;
+                    const uint32_t o = second ? lane - cA : lane;
+                    e[u] = 0;
+                    if (lane < tot[u])
+                        e[u] = (tile_smem[second ? 1 : 0] + 2 * S)[(second ? sB : sA) + o];
+                    at[u] = (second ? gB : gA) + o;
+                    e[u] = idx0[second ? 1 : 0] + (e[u] & 0xffffu);
+                }
+                #pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    if (lane < tot[u])
+                        p.perm[at[u]] = e[u];
+                    // rare: more than 32 entries in the two runs together
+                    for (uint32_t off = lane + 32; off < tot[u]; off += 32) {
+                        const bool second = off >= cAs[u];
+                        const uint32_t o = second ? off - cAs[u] : off;
+                        const uint32_t v = (tile_smem[second ? 1 : 0] + 2 * S)[(second ? sBs[u] : sAs[u]) + o];
+                        p.perm[(second ? gBs[u] : gAs[u]) + o] = idx0[second ? 1 : 0] + (v & 0xffffu);
+                    }
+                }
+            }
+        }
+        cluster.sync();             // the other CTA has read my staged entries: the buffers are free again
+    }
+}
+
+#endif // DRJIT_B200_EXPERIMENTS (pair kernel)
+
+#if defined(DRJIT_B200_EXPERIMENTS)
+// ---------------------------------------------------------------------------
 //  Unordered tile scatter with 16-bit staging entries (EXPERIMENTAL: DRJIT_B200_MKPERM_KPT=60)
 // ---------------------------------------------------------------------------
 //  DESIGN.md section 8.1, step (1). The staged entry is the key's 16-bit local index only, which
@@ -1203,6 +1397,15 @@ static bool use_tile_path(uint32_t n_groups, uint32_t size, uint32_t bucket_coun
            tiles * bucket_count * 6 <= ((uint64_t) 2 << 30);
 }
 
+#if defined(DRJIT_B200_EXPERIMENTS)
+/// Cluster-of-two scatter kernel (mkperm_tile_scatter_pair_kernel): measured slower, kept for A/B
+/// runs in experiments builds (DRJIT_B200_MKPERM_PAIR=1)
+static bool use_pair_kernel(const MkpermTileParams &t) {
+    static const int pair = env_int("DRJIT_B200_MKPERM_PAIR", 0);
+    return pair != 0 && t.n_pay == 0;
+}
+#endif
+
 template <uint32_t THREADS, uint32_t KEY_BITS>
 static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t, uint32_t grid, uint32_t smem, uint32_t smem_max) {
     static std::atomic<bool> configured_on[kMaxDevices] = {};       // (function attributes are per device)
@@ -1320,6 +1523,34 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     } else {
         const uint32_t ctas = std::max(1u, std::min(1024 / THREADS, (dev.smem_optin + 1024) / (scatter_smem + 1024)));
         const uint32_t grid = std::min(t.tiles, dev.sm_count * ctas);
+#if defined(DRJIT_B200_EXPERIMENTS)
+        if constexpr (!STABLE && THREADS == 1024 && KPT >= 40) {
+            if (use_pair_kernel(t)) {
+                // clusters of two CTAs, two consecutive tiles per cluster and round
+                static std::atomic<bool> pair_configured_on[kMaxDevices] = {};
+                std::atomic<bool> &pc = pair_configured_on[dev.device % kMaxDevices];
+                if (!pc.load(std::memory_order_acquire)) {
+                    DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_pair_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4, dev.smem_optin - 1024)));
+                    pc.store(true, std::memory_order_release);
+                }
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(2 * std::max(1u, std::min((t.tiles + 1) / 2, dev.sm_count / 2)));
+                cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = scatter_smem; cfg.stream = stream;
+                cudaLaunchAttribute attr{};
+                attr.id = cudaLaunchAttributeClusterDimension;
+                attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+                cfg.attrs = &attr; cfg.numAttrs = 1;
+                DJB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mkperm_tile_scatter_pair_kernel<THREADS, KPT>, t));
+                DJB_POST_LAUNCH();
+                if (!want_table)
+                    return 0;
+                scratch.unlock();
+                DJB_CUDA_CHECK(cudaEventSynchronize(ev));
+                return pinned[1];
+            }
+        }
+#endif
 #if defined(DRJIT_B200_EXPERIMENTS)
         if constexpr (STAGE16)
             mkperm_tile_scatter16_kernel<THREADS, KPT><<<std::min(t.tiles, dev.sm_count), THREADS, scatter_smem, stream>>>(t);
