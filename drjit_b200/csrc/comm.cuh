@@ -172,9 +172,15 @@ __device__ __forceinline__ A peer_fold_scalar(const PeerCtx &c, A mine, uint32_t
     A acc = Op::template identity<A>();
     const uint32_t lo = fold == kFoldHigher ? c.rank + 1 : 0u,
                    hi = fold == kFoldLower ? c.rank : c.world;
-    for (uint32_t src = lo; src < hi; ++src) {
+    // Every rank observes EVERY peer's cell of this epoch, also those its fold does not use: the two
+    // cell parities are only safe while no rank runs more than one epoch ahead of any other. A rank
+    // that skipped the wait (rank 0 of a lower-ranks fold needs no value at all) could publish epoch
+    // e + 2 over a cell of epoch e that a slower peer has not read yet -- that peer would then spin
+    // for an epoch it can never see (found at world 2 with three scans in a row, profiles/r5_n8*).
+    for (uint32_t src = 0; src < c.world; ++src) {
         pay.u = peer_get_u64(c, epoch, src);
-        acc = Op::template apply<A>(acc, pay.a);
+        if (src >= lo && src < hi)
+            acc = Op::template apply<A>(acc, pay.a);
     }
     peer_end(c, epoch);
     return acc;

@@ -110,3 +110,42 @@ def test_allreduce_bins_sizes_and_types(world):
     res = _run_world(world, 0, body)
     for r in res[1:]:
         assert all(torch.equal(a, b) for a, b in zip(r, res[0]))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_consecutive_one_sided_folds_never_overrun_a_slow_peer(world):
+    """A lower-ranks fold needs no value on rank 0 and an upper-ranks fold none on the last rank. Every
+    rank must still observe all peers in every epoch: with two cell parities a rank that ran two
+    epochs ahead would overwrite a cell its peer has not read yet (the peer then waits for an epoch it
+    can never see and traps after 20 s). Rank 0 enqueues 64 folds back to back while the other ranks
+    are held back by a long-running kernel in front of theirs."""
+    from drjit_b200.ops import ReduceOp, VarType
+
+    def body(sh, rank, world, dev, n):
+        K = 64
+        src = [torch.tensor([(rank + 1) * (k + 1)], dtype=torch.int32, device=dev) for k in range(K)]
+        low = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(K)]
+        high = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(K)]
+        torch.cuda.synchronize(dev)
+        for lower, dst in ((True, low), (False, high)):
+            slow = 0 if not lower else world - 1        # the rank whose values everybody else needs last
+            if rank == slow and world > 1:
+                torch.cuda._sleep(200_000_000)           # ~0.1 s on the stream in front of the folds
+            for k in range(K):
+                if lower:
+                    sh.fold_scalar(ReduceOp.Add, src[k], dst[k], lower=True, vt=VarType.UInt32)
+                else:   # upper-ranks fold: what a reverse scan uses (FOLD_HIGHER through the scan entry point)
+                    x = torch.full((8,), (rank + 1) * (k + 1), dtype=torch.int32, device=dev)
+                    import ctypes
+                    from drjit_b200._lib import check, lib
+                    out = torch.empty_like(x)
+                    check(lib.drjit_b200_comm_prefix_reduce(
+                        sh.comm.ptr, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), int(VarType.UInt32),
+                        int(ReduceOp.Add), 8, 1, 1, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                        ctypes.c_void_p(dst[k].data_ptr()), 0))
+            torch.cuda.synchronize(dev)
+        for k in range(K):
+            assert int(low[k].cpu()[0]) == sum((r + 1) * (k + 1) for r in range(rank))
+            assert int(high[k].cpu()[0]) == sum(8 * (r + 1) * (k + 1) for r in range(rank + 1, world))
+
+    _run_world(world, 0, body)
