@@ -151,13 +151,28 @@ __global__ void __launch_bounds__(kBulkThreads) peer_allreduce_kernel(const Peer
         const uint64_t lo = (uint64_t) r * per;
         return lo >= n ? 0u : (uint32_t) min((uint64_t) per, (uint64_t) n - lo);
     };
-    // whole vectors of a slice + scalar tail (only the last non-empty slice has one; `data` is 16-byte aligned)
-    auto copy = [&](T *dst, const T *src, uint32_t len) {
-        const uint32_t nvec = len / V;
-        for (uint64_t i = gtid; i < nvec; i += gstride)
-            reinterpret_cast<uint4 *>(dst)[i] = __ldcg(reinterpret_cast<const uint4 *>(src) + i);
-        for (uint64_t i = (uint64_t) nvec * V + gtid; i < len; i += gstride)
-            dst[i] = __ldcg(src + i);
+    // The W - 1 foreign slices move as ONE flat loop over (peer, vector) pairs: every thread of the grid
+    // has stores to some peer in flight at the same time (a loop per peer left more than half of the
+    // grid idle on every 512 KiB slice and paid one remote latency per peer: 54 us for 4 MB at 8
+    // ranks, profiles/r5_n8_time_sharded_n8.txt). A slice's ragged last vector goes element-wise
+    // (only the last non-empty slice has one; `data` and all window regions are 16-byte aligned).
+    //   dst_of(p), src_of(p): base pointers of slice p's destination / source
+    auto copy_foreign = [&](auto dst_of, auto src_of) {
+        const uint32_t vps = per / V;                                   // vectors per slice
+        const uint64_t total = (uint64_t) (W - 1) * vps;
+        for (uint64_t j = gtid; j < total; j += gstride) {
+            const uint32_t i = (uint32_t) (j / vps), v = (uint32_t) (j - (uint64_t) i * vps);
+            const uint32_t q = (me + 1 + i) % W, len = slice_len(q);
+            if (v * V >= len)
+                continue;
+            T *dst = dst_of(q); const T *src = src_of(q);
+            if ((v + 1) * V <= len) {
+                reinterpret_cast<uint4 *>(dst)[v] = __ldcg(reinterpret_cast<const uint4 *>(src) + v);
+            } else {
+                for (uint32_t e = v * V; e < len; ++e)
+                    dst[e] = __ldcg(src + e);
+            }
+        }
     };
     // all CTAs have arrived at counter `which`; the last one raises flag `which + 1` at every peer
     auto grid_arrive_and_flag = [&](uint32_t which) {
@@ -183,11 +198,8 @@ __global__ void __launch_bounds__(kBulkThreads) peer_allreduce_kernel(const Peer
     };
 
     // ---- phase 1: push my copy of every foreign slice ------------------------------------------
-    for (uint32_t i = 1; i < W; ++i) {
-        const uint32_t p = (me + i) % W;
-        T *dst = reinterpret_cast<T *>(c.win[p] + kWinBulkOffset + me * staging_stride);
-        copy(dst, data + (uint64_t) p * per, slice_len(p));
-    }
+    copy_foreign([&](uint32_t q) { return reinterpret_cast<T *>(c.win[q] + kWinBulkOffset + me * staging_stride); },
+                 [&](uint32_t q) { return (const T *) (data + (uint64_t) q * per); });
     grid_arrive_and_flag(0);
     wait_flags(0);
 
@@ -233,11 +245,8 @@ __global__ void __launch_bounds__(kBulkThreads) peer_allreduce_kernel(const Peer
     wait_flags(1);
 
     // ---- phase 3: collect the foreign result slices ----------------------------------------------
-    for (uint32_t i = 1; i < W; ++i) {
-        const uint32_t p = (me + i) % W;
-        const T *src = reinterpret_cast<const T *>(c.win[me] + kWinBulkOffset + c.bulk_bytes + p * staging_stride);
-        copy(data + (uint64_t) p * per, src, slice_len(p));
-    }
+    copy_foreign([&](uint32_t q) { return data + (uint64_t) q * per; },
+                 [&](uint32_t q) { return reinterpret_cast<const T *>(c.win[me] + kWinBulkOffset + c.bulk_bytes + q * staging_stride); });
     __syncthreads();
     if (tid == 0) {
         const uint32_t prev = atomicAdd(counters + 2, 1u);
@@ -257,7 +266,8 @@ template <typename T> static void launch_allreduce(cudaStream_t stream, const Pe
               (unsigned long long) ((uint64_t) per * sizeof(T) * c.world), (unsigned long long) c.bulk_bytes);
     const DeviceProps &dev = device_props();
     // enough CTAs to drive NVLink (each moves 16 B per thread and round), never more than one per SM
-    uint32_t grid = std::max(1u, std::min(dev.sm_count, ceil_div(per / V, kBulkThreads)));
+    // (the push / collect phases move W - 1 slices per rank)
+    uint32_t grid = std::max(1u, std::min(dev.sm_count, ceil_div((c.world - 1) * (per / V), kBulkThreads)));
     T *d = (T *) data;
     void *args[] = { (void *) &c, (void *) &d, (void *) &n, (void *) &per };
     DJB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *) peer_allreduce_kernel<T>, dim3(grid), dim3(kBulkThreads),

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "comm.cuh"
 
 namespace djb {
 
@@ -44,7 +45,27 @@ struct CompressParams {
     uint32_t *count_out;  // device-accessible
     uint32_t size, tiles, index_base;
     uint32_t debug;       // read only in -DDRJIT_B200_EXPERIMENTS builds (scripts/sweep_compress.cu): 1 = carry chain disabled
+    // PEER instantiations (sharded masks, comm_compress): the thread that learns the shard's count
+    // exchanges it with the other ranks through the communicator's scalar cells and writes all W
+    // counts, followed by the call's sequence number, into pinned host memory. No second launch, and
+    // the host is told when the last tile STARTS its compaction -- it does not wait for the kernel
+    // to drain and for the stream's completion signal.
+    PeerCtx peer;
+    uint32_t *host_counts;  // device view of kMaxPeers + 1 pinned words: counts[0..world), [kMaxPeers] = seq
+    uint32_t seq;
 };
+
+/// One thread: all-gather of the per-rank counts straight into pinned host memory, then the
+/// sequence word the host spins on (also used by the one-thread kernel of an empty shard)
+__device__ __forceinline__ void peer_publish_counts(const PeerCtx &c, uint32_t mine, uint32_t *host_counts, uint32_t seq) {
+    const uint32_t epoch = peer_begin(c);
+    peer_put_u64(c, epoch, mine);
+    for (uint32_t src = 0; src < c.world; ++src)
+        host_counts[src] = (uint32_t) peer_get_u64(c, epoch, src);
+    peer_end(c, epoch);
+    __threadfence_system();                         // counts before the sequence word
+    *reinterpret_cast<volatile uint32_t *>(host_counts + kMaxPeers) = seq;
+}
 
 constexpr uint32_t kCompWindowLoads = 3;                     // carry window: grids of up to 768 CTAs
 constexpr uint32_t kComp2RowStride = kCompRowSlots;          // u16 entries per warp staging row
@@ -102,7 +123,7 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
 
 /// COPY: kCopyLsu / kCopyBulk. BASE512: p.index_base is a multiple of 512, so that the index of an
 /// entry is the OR of (row base | lane * 16 | position nibble) -- no add per entry (kCopyBulk only).
-template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t COPY = kCopyLsu, bool BASE512 = true>
+template <uint32_t ROWS, uint32_t STAGES, uint32_t MIN_CTAS, uint32_t COPY = kCopyLsu, bool BASE512 = true, bool PEER = false>
 __global__ void __launch_bounds__(kCompThreads, MIN_CTAS)
 compress_kernel(const CompressParams p) {
     static_assert(ROWS % 2 == 0, "rows are ranked in pairs");
@@ -275,6 +296,8 @@ compress_kernel(const CompressParams p) {
             #pragma unroll
             for (uint32_t w = 0; w < kCompWarps; ++w) ttotal += wcnt[it % 4][w];
             *p.count_out = carry + ttotal;
+            if constexpr (PEER)
+                peer_publish_counts(p.peer, carry + ttotal, p.host_counts, p.seq);
         }
 
         // ---- compaction of tile `it` -----------------------------------------------------------

@@ -288,8 +288,12 @@ class Sharded:
     # ------------------------------------------------------------------ compress
     def compress(self, mask, index_base, out=None):
         """Shard-local compaction with global indices. Returns (out, counts): rank r owns
-        out[:counts[r]]; the global list is the rank-order concatenation. Like the reference
-        (cuda_ts.cpp:759) the call ends with one host synchronisation to read the counts."""
+        out[:counts[r]]; the global list is the rank-order concatenation. The call blocks until the
+        counts are known. Fused path: ONE launch -- the thread of the compaction kernel that learns the
+        shard's count exchanges it over NVLink and writes all W counts into pinned host memory, the
+        host spins on a sequence word; like jit_block_mkperm (cuda_ts.cpp:953-967) the call returns
+        once the host-visible part of the result is there, ``out`` is complete in stream order.
+        Collective path: compress_async + all-gather + one host synchronisation."""
         if self.comm is not None:
             if out is None:
                 out = torch.empty(mask.numel(), dtype=torch.int32, device=mask.device)

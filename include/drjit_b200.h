@@ -389,7 +389,10 @@ DRJIT_B200_API int drjit_b200_comm_prefix_reduce(void *comm, void *stream, int v
                                                  int exclusive, int reverse, const void *in, void *out,
                                                  void *offset_out, int materialise);
 /* jit_compress of this rank's shard (indices are index_base + local index) and the exchange of the
- * per-rank counts: counts_host[0..world) (host). Synchronous like the reference. */
+ * per-rank counts: counts_host[0..world) (host). One launch: the exchange happens inside the
+ * compaction kernel, which writes the W counts to pinned host memory. The call blocks until the counts
+ * are there and returns them; `out` is complete in stream order (the contract jit_block_mkperm has for
+ * `perm`, cuda_ts.cpp:953-967), so anything enqueued on `stream` afterwards sees the full list. */
 DRJIT_B200_API int drjit_b200_comm_compress(void *comm, void *stream, const uint8_t *in, uint32_t size,
                                             uint32_t index_base, uint32_t *out, uint32_t *counts_host);
 /* jit_block_mkperm of one sorting group sharded over the ranks: perm (device, `size` entries) = this

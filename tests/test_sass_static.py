@@ -16,7 +16,7 @@ LIB = os.path.join(ROOT, "drjit_b200", "lib", "libdrjit_b200.so")
 pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
 
 SCAN = "_ZN3djb20prefix_reduce_kernelIjNS_5OpAddELb0ELb1ELj8ELj3ELj2EEEvNS_12PrefixParamsE"
-COMPRESS = "_ZN3djb15compress_kernelILj8ELj1ELj3ELj3ELb1EEEvNS_14CompressParamsE"
+COMPRESS = "_ZN3djb15compress_kernelILj8ELj1ELj3ELj3ELb1ELb0EEEvNS_14CompressParamsE"
 SUM = "_ZN3djb25block_reduce_chunk_kernelIfNS_5OpAddELb0ELb1ELb0EEEvPKT_S4_PS2_PNS_3AccIS2_E4typeEPjjjjjNS_7PeerCtxEj"
 SUM_PEER = SUM.replace("ELb0ELb1ELb0EEE", "ELb0ELb1ELb1EEE")
 MKPERM_SCATTER = "_ZN3djb26mkperm_tile_scatter_kernelILj1024ELj%uEEEvNS_16MkpermTileParamsE"
