@@ -43,11 +43,8 @@ SUITE = [
     ("sum_f32", 28, 4.0, "block_reduce_chunk_kernel<f32,Add>"),
     ("block_reduce256_f32", 28, 4.0 + 4.0 / 256, "block_reduce_group_kernel<f32,Add,16 lanes>"),
     ("dot_f32", 28, 8.0, "block_reduce_chunk_kernel<f32,Add,dot>"),
-    # (order inside a step: the read-only, HBM-bound kernels first; the scan's 4 GB of output leave the L2
-    #  full of dirty lines whose write-back the next kernel shares the bandwidth with -- mkperm, which is
-    #  not HBM-bound, follows it)
-    ("compress_u8", 30, 3.0, "compress_kernel<8,1,3,kCopyLsuPairs>"),          # 1 + 4 * density, density = 0.5
     ("prefix_sum_u32", 30, 8.0, "prefix_reduce_kernel<u32,Add>"),
+    ("compress_u8", 30, 3.0, "compress_kernel<8,1,3,kCopyLsuPairs>"),          # 1 + 4 * density, density = 0.5
     ("mkperm_4096", 26, 12.0, "mkperm_tile_hist_kernel + column/bucket scan kernels + mkperm_tile_scatter_kernel<1024,48>"),
     ("scatter_add_f32", 28, 8.0, "scatter_reduce_kernel<f32,Add>"),
 ]
@@ -377,7 +374,10 @@ def make_prims(wl, sh, ops, ReduceOp, VarType, results):
                                                        vt=VarType.UInt32, out=wl.u_out), None)
 
     def p_compress():
-        results["count"] = sh.compress(wl.mask, wl.range["compress_u8"][0] & 0xFFFFFFFF, out=wl.c_out)
+        if world > 1:
+            results["count"] = sh.compress(wl.mask, wl.range["compress_u8"][0] & 0xFFFFFFFF, out=wl.c_out)
+        else:           # the seam function (cuda_ts.cpp:683-763): one launch, count read from pinned memory after the wait
+            results["count"] = (wl.c_out, [ops.compress_into(wl.mask, wl.c_out)])
 
     def p_mkperm():
         if world > 1:
@@ -391,7 +391,7 @@ def make_prims(wl, sh, ops, ReduceOp, VarType, results):
         results["bins"] = sh.scatter_add(wl.bins_t, wl.sval, wl.sidx)
 
     return [("sum_f32", p_sum), ("block_reduce256_f32", p_block_reduce), ("dot_f32", p_dot),
-            ("compress_u8", p_compress), ("prefix_sum_u32", p_prefix), ("mkperm_4096", p_mkperm),
+            ("prefix_sum_u32", p_prefix), ("compress_u8", p_compress), ("mkperm_4096", p_mkperm),
             ("scatter_add_f32", p_scatter)]
 
 
@@ -745,31 +745,6 @@ def main():
         dist.destroy_process_group()
 
 
-_WC_KEEP = []
-
-
-def pinned_upload_buffer(torch, like):
-    """Pinned host buffer an input is uploaded from. DRJIT_B200_E2E_WC=1: write-combined pinned memory
-    (cudaHostAlloc + cudaHostAllocWriteCombined: the device reads it over PCIe without snooping the CPU
-    caches; the CPU only ever writes it) instead of torch's cacheable pinned memory -- an A/B switch,
-    the JSON names what was used."""
-    if os.environ.get("DRJIT_B200_E2E_WC", "0") != "1":
-        return torch.empty(like.shape, dtype=like.dtype).pin_memory()
-    import ctypes
-    import numpy as np
-    rt = ctypes.CDLL("libcudart.so.12")
-    nbytes = like.numel() * like.element_size()
-    ptr = ctypes.c_void_p()
-    rv = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(max(nbytes, 16)), ctypes.c_uint(0x04))
-    if rv != 0:
-        raise SystemExit(f"bench.py: cudaHostAlloc(write-combined, {nbytes} bytes) failed with {rv}")
-    buf = (ctypes.c_uint8 * max(nbytes, 16)).from_address(ptr.value)
-    _WC_KEEP.append((rt, ptr, buf))             # (never freed: the process ends with the bench)
-    t = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8, count=nbytes)).view(like.dtype).view(like.shape)
-    assert t.is_pinned()
-    return t
-
-
 def run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, total_bytes):
     """Same suite, but every step first copies the step's inputs host->device from pinned
     memory and afterwards reads every primitive's result back to the host."""
@@ -780,7 +755,7 @@ def run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, to
     wl.x_br = wl.x_dot = wl.x
     inputs = dict(x=wl.x, y=wl.y, u=wl.u, mask=wl.mask, keys=wl.keys, sidx=wl.sidx, sval=wl.sval)
     outputs = dict(u_out=wl.u_out, c_out=wl.c_out, perm=wl.perm, bins_t=wl.bins_t, br_out=wl.br_out)
-    host_in = {k: pinned_upload_buffer(torch, v) for k, v in inputs.items() if k != "sval" or v is not wl.x}
+    host_in = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in inputs.items() if k != "sval" or v is not wl.x}
     for k, h in host_in.items():
         h.copy_(inputs[k])
     host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outputs.items()}
@@ -915,7 +890,6 @@ def run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, to
             "d2h_bytes_per_step": d2h_all, "ms_per_step": round(dt * 1e3, 3), "steps": steps,
             "pcie_GBps": {"h2d": round(h2d_all / dt / 1e9, 1), "d2h": round(d2h_all / dt / 1e9, 1),
                           "note": "all ranks together, per direction, averaged over the step"},
-            "upload_buffers": "write-combined pinned" if os.environ.get("DRJIT_B200_E2E_WC", "0") == "1" else "pinned",
             "note": "per rank: pinned host inputs -> device, suite through the public API, every result "
                     "(scalars, block sums, scan, index list, permutation, bins) -> pinned host; uploads, "
                     "kernels and downloads pipelined on three streams (downloads of a step overlap the uploads of "

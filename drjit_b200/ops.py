@@ -269,6 +269,20 @@ def compress(mask):
     return res.view(idx_dtype) if idx_dtype is not torch.int32 else res
 
 
+def compress_into(mask, out):
+    """jit_compress() as the seam has it (cuda_ts.cpp:683-763): indices into the caller's buffer
+    ``out`` (at least mask.numel() int32 entries), returns the count after the synchronisation."""
+    m = _check_array(mask, "mask")
+    if m.dtype not in (torch.bool, torch.uint8):
+        raise RuntimeError("drjit_b200: compress() expects a boolean mask")
+    if out.numel() < m.numel() or out.element_size() != 4:
+        raise RuntimeError("drjit_b200: compress_into() needs an output buffer of mask.numel() 32-bit entries")
+    count = ctypes.c_uint32(0)
+    with _on(m.device):
+        check(lib.drjit_b200_compress(_stream(m), _ptr(m), m.numel(), _ptr(out), ctypes.byref(count)))
+    return count.value
+
+
 # --------------------------------------------------------------------------- mkperm
 _pinned_cache = {}
 
