@@ -41,7 +41,10 @@ def main():
             if m and func:
                 table[func][int(m.group(1), 16)] = cur
 
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # source page exported on the GPU box (`ncu -i rep --page source --csv`)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     # the csv holds one block per launch: "Kernel Name", name / header / rows
     blocks, cur = [], None
     for row in csv.reader(io.StringIO(out)):

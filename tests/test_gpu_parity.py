@@ -331,6 +331,29 @@ def test_block_prefix_reduce_short_blocks(vt):
         assert np.array_equal(to_np(y, vt), exp)
 
 
+@pytest.mark.parametrize("vt", ["u8", "f16", "i32", "u32", "f32", "u64", "f64"])
+def test_block_prefix_reduce_medium_blocks(vt):
+    """blocks of 9 .. 32 Ki elements on arrays large enough for the group-per-block kernel (a group of
+    2..32 lanes walks one block; blocks start inside 16-byte units, the last block is ragged): all four
+    variants, several ops, in place; blocks past the kernel's limit fall through to the general path."""
+    size = 3_000_017 if vt != "u8" else 6_000_029
+    x = make_input(vt, size); xd = to_dev(x, vt)
+    ops_for = ["add", "max"] + ([] if vt[0] == "f" else ["and"])
+    for bs in [9, 17, 33, 100, 1000, 4099, 32768, 70001]:
+        for op in ops_for:
+            for ex, rev in ((0, 0), (1, 0), (0, 1), (1, 1)):
+                got = to_np(dr.block_prefix_reduce(OPS[op], xd, bs, ex, rev, vt=VT[vt]), vt)
+                exp = capi.block_prefix_reduce(vt, op, x, bs, ex, rev, acc64=(vt[0] == "f"))
+                if vt[0] == "f" and op == "add":
+                    assert_close(got, exp, vt, bs, f"{vt} prefix bs={bs} size={size}")
+                else:
+                    assert np.array_equal(got, exp), (vt, op, bs, ex, rev)
+    for bs, ex, rev in ((1000, True, False), (37, False, True)):
+        y = xd.clone()
+        dr.block_prefix_reduce(OPS["max"], y, bs, ex, rev, vt=VT[vt], out=y)
+        assert np.array_equal(to_np(y, vt), capi.block_prefix_reduce(vt, "max", x, bs, ex, rev)), ("in place", bs)
+
+
 @pytest.mark.parametrize("vt", ["u8", "u32", "u64", "i32", "i64"])
 def test_prefix_windowed_carry_many_tiles(vt):
     """Unsegmented scans on the TMA path with more tiles than CTAs (every CTA advances its carry
