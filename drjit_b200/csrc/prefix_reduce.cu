@@ -139,137 +139,6 @@ static uint64_t try_prefix_short_blocks(cudaStream_t stream, const PrefixParams 
     return n_groups * bs * V;
 }
 
-// ---------------------------------------------------------------------------
-//  Medium blocks (up to 32 Ki elements): every block is scanned by a group of G lanes
-// ---------------------------------------------------------------------------
-//  dr.block_prefix_sum / cumsum along a trailing axis of a few to a few thousand entries. Blocks are
-//  independent, so nothing has to travel between CTAs: a group of G lanes (G = 2..32, a power of two
-//  chosen from the block size) walks one block in chunks of G 128-bit units -- unit-local scan in
-//  registers, one log2(G)-step shuffle scan, running carry in a register -- and a warp holds 32 / G
-//  blocks at once. No tiles, no descriptors, no shared memory, no barriers, and none of the
-//  per-element head arithmetic of the general segmented kernel (which runs at 44 % of the copy
-//  bandwidth for blocks of 1000 f32, profiles/r5a_prims.txt). Units are aligned to the array base,
-//  not to the block: the first and last unit of a block may be shared with its neighbours; foreign
-//  elements enter the scan as the identity and are not stored (scalar stores at the ragged ends,
-//  STG.128 everywhere else), so in-place operation stays safe. The next chunk's unit is loaded
-//  before the current one is scanned (two 16-byte loads in flight per lane).
-constexpr uint32_t kGroupBlocksMaxBytes = 128 * 1024;
-
-template <typename T, typename Op>
-__global__ void __launch_bounds__(256)
-prefix_group_blocks_kernel(const T *in, T *out, uint32_t size, uint32_t bs, uint32_t n_blocks,
-                           uint32_t G, uint32_t iters, uint32_t exclusive, uint32_t reverse) {
-    using A = acc_t<T>;
-    constexpr uint32_t V = 16 / sizeof(T);
-    const A ident = Op::template identity<A>();
-    const uint32_t lane = threadIdx.x & 31u, gl = lane & (G - 1u), sub = lane / G, gpw = 32u / G;
-    const uint64_t warp = ((uint64_t) blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (uint64_t) gridDim.x * 8;
-
-    // (all lanes of a warp run the same number of rounds and chunks: the shuffles are warp-wide)
-    for (uint64_t b0 = warp * gpw; b0 < n_blocks; b0 += n_warps * gpw) {
-        const uint64_t b = b0 + sub;
-        const bool active = b < n_blocks;
-        const uint64_t start = active ? b * bs : 0,
-                       end = active ? (start + bs < size ? start + bs : (uint64_t) size) : 0;
-        const uint64_t u0 = start / V, u1 = active ? (end - 1) / V : 0;
-        const uint32_t n_units = active ? (uint32_t) (u1 - u0) + 1u : 0u;
-
-        // unit k of the block in scan order (mirrored for reverse scans)
-        auto load = [&](uint32_t k, Vec16<T> &raw) {
-            if (k >= n_units)
-                return;
-            const uint64_t base = (reverse ? u1 - k : u0 + k) * V;
-            if (base + V <= size) {
-                raw = ld_vec<T>(in + base);                 // (coherent: `out` may alias `in`)
-            } else {
-                #pragma unroll
-                for (uint32_t e = 0; e < V; ++e)
-                    raw.v[e] = base + e < size ? in[base + e] : T();
-            }
-        };
-
-        A carry = ident;
-        Vec16<T> cur{}, nxt{};
-        load(gl, cur);
-        for (uint32_t it = 0; it < iters; ++it) {
-            const uint32_t k = it * G + gl;
-            if (it + 1 < iters)
-                load(k + G, nxt);
-            const bool valid = k < n_units;
-            const uint64_t base = valid ? (reverse ? u1 - k : u0 + k) * V : 0;
-
-            // unit-local inclusive scan in scan order; foreign / out-of-range elements are the identity
-            A incl[V];
-            A run = ident;
-            #pragma unroll
-            for (uint32_t e = 0; e < V; ++e) {
-                const uint32_t ee = reverse ? V - 1 - e : e;            // element of the unit
-                const uint64_t pos = base + ee;
-                const T raw_e = reverse ? cur.v[V - 1 - e] : cur.v[e];
-                const A x = (valid && pos >= start && pos < end) ? to_acc<A>(raw_e) : ident;
-                run = Op::template apply<A>(run, x);
-                incl[e] = run;
-            }
-            // scan of the unit totals over the group's lanes
-            A v = run;
-            for (uint32_t d = 1; d < G; d <<= 1) {
-                const A t = __shfl_up_sync(kFullMask, v, d, G);
-                if (gl >= d) v = Op::template apply<A>(t, v);
-            }
-            A ex = __shfl_up_sync(kFullMask, v, 1, G);
-            if (gl == 0) ex = ident;
-            const A chunk_total = __shfl_sync(kFullMask, v, G - 1u, G);
-            const A prefix = Op::template apply<A>(carry, ex);
-            carry = Op::template apply<A>(carry, chunk_total);
-
-            if (valid) {
-                Vec16<T> o;
-                #pragma unroll
-                for (uint32_t e = 0; e < V; ++e) {
-                    const A r = exclusive ? (e == 0 ? prefix : Op::template apply<A>(prefix, incl[e ? e - 1 : 0]))
-                                          : Op::template apply<A>(prefix, incl[e]);
-                    if (reverse) o.v[V - 1 - e] = from_acc<T>(r);
-                    else         o.v[e] = from_acc<T>(r);
-                }
-                if (base >= start && base + V <= end) {
-                    *reinterpret_cast<uint4 *>(out + base) = *reinterpret_cast<const uint4 *>(&o);
-                } else {
-                    #pragma unroll
-                    for (uint32_t e = 0; e < V; ++e)
-                        if (base + e >= start && base + e < end)
-                            out[base + e] = o.v[e];
-                }
-            }
-            cur = nxt;
-        }
-    }
-}
-
-/// True if the group kernel took the call
-template <typename T, typename Op>
-static bool try_prefix_group_blocks(cudaStream_t stream, const PrefixParams &p) {
-    constexpr uint32_t V = 16 / sizeof(T);
-    const uint32_t bs = p.block_size;
-    if (bs < 2 || bs >= p.size || (uint64_t) bs * sizeof(T) > kGroupBlocksMaxBytes || p.carry_in || p.total_out ||
-        ((uintptr_t) p.in % 16) || ((uintptr_t) p.out % 16))
-        return false;
-    const uint32_t units_max = ceil_div(bs, V) + 1;         // a block that starts inside a unit touches one more
-    uint32_t G = 2;
-    while (G < 32 && G < units_max) G <<= 1;
-    const uint32_t iters = ceil_div(units_max, G);
-    const uint32_t n_blocks = ceil_div(p.size, bs);
-    const uint64_t warps = ceil_div64(n_blocks, 32 / G);
-    const DeviceProps &dev = device_props();
-    // long blocks need enough of them to fill the machine: a warp walks its block chunk by chunk
-    if (iters > 4 && warps < (uint64_t) dev.sm_count * 4)
-        return false;
-    const uint32_t grid = (uint32_t) std::min<uint64_t>(ceil_div64(warps, 8), (uint64_t) dev.sm_count * 8);
-    prefix_group_blocks_kernel<T, Op><<<grid, 256, 0, stream>>>((const T *) p.in, (T *) p.out, p.size, bs, n_blocks,
-                                                                G, iters, p.exclusive, p.reverse);
-    DJB_POST_LAUNCH();
-    return true;
-}
-
 template <typename T, typename Op>
 static void launch_prefix(cudaStream_t stream, PrefixParams &p) {
     constexpr uint32_t V = 16 / sizeof(T);
@@ -285,8 +154,6 @@ static void launch_prefix(cudaStream_t stream, PrefixParams &p) {
         if (p.block_size > p.size) p.block_size = p.size;
     }
     const bool seg = p.block_size < p.size;
-    if (seg && try_prefix_group_blocks<T, Op>(stream, p))
-        return;
     // 128-bit / TMA path: both pointers 16-byte aligned; mirrored (reverse) vectors additionally
     // need the array end to fall on a vector boundary.
     const bool vec = ((uintptr_t) p.in % 16) == 0 && ((uintptr_t) p.out % 16) == 0 &&
@@ -369,6 +236,12 @@ void block_prefix_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uin
         }
         return;
     }
+
+    // Medium blocks: a group of lanes per block (prefix_group.cu). Blocks of 2..8 elements of large
+    // arrays stay with the thread-per-block kernel below (copy speed).
+    if (block_size < size && !carry_in && !total_out && !(block_size <= 8 && size >= (1u << 16)) &&
+        prefix_group_blocks(stream, vt, op, size, block_size, exclusive, reverse, in, out))
+        return;
 
     PrefixParams p{};
     p.in = in; p.out = out; p.size = size; p.block_size = block_size;
