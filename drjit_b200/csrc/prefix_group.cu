@@ -28,7 +28,8 @@
 
 namespace djb {
 
-constexpr uint32_t kGroupBlocksMaxBytes = 128 * 1024;
+constexpr uint32_t kGroupBlocksMaxBytes = 1024 * 1024;
+constexpr uint32_t kGroupBlocksFewBytes = 128 * 1024;  // longer blocks only with a warp on (nearly) every scheduler slot
 constexpr uint32_t kGroupThreads = 256;
 constexpr uint32_t kGroupDepth = 4;         // units in flight per lane (register ring)
 
@@ -190,7 +191,11 @@ static bool group_dispatch(cudaStream_t stream, uint32_t size, uint32_t bs, bool
     const uint64_t warps = ceil_div64(n_blocks, 32 / G);
     const DeviceProps &dev = device_props();
     // long blocks need enough of them to fill the machine: a warp walks its block chunk by chunk
-    if (iters > 4 && warps < (uint64_t) dev.sm_count * 4)
+    // (a warp has three 512-byte loads in flight: a quarter of the resident warps cannot fill the memory
+    //  pipeline alone, but their blocks are short enough for the tail not to matter; blocks beyond 128 KiB
+    //  need half of the 32 warps per SM that fit)
+    const uint32_t min_warps_per_sm = (uint64_t) bs * sizeof(T) > kGroupBlocksFewBytes ? 16u : 4u;
+    if (iters > 4 && warps < (uint64_t) dev.sm_count * min_warps_per_sm)
         return false;
     // Lane slots that carry data. Short blocks leave lanes idle (a block of 9 f32 fills 2.25 of its 4
     // lanes' units) while the general kernel's cost per element does not depend on the block size: below

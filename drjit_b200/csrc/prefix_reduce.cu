@@ -48,6 +48,9 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     // outputs of at least twice the L2 size cannot stay resident anyway (smaller ones are left to the
     // default policy: a consumer kernel finds them in L2)
     p.evict_first = (uint64_t) p.size * sizeof(T) >= ((uint64_t) 256 << 20);
+#if defined(DJB_AB_NO_EVICT_FIRST)
+    p.evict_first = 0;          // (A/B build of the shipped configuration: make AB=... in csrc/Makefile)
+#endif
 #if defined(DRJIT_B200_EXPERIMENTS)
     if (const char *env = getenv("DRJIT_B200_SCAN_EVICT_FIRST")) p.evict_first = atoi(env) != 0;    // A/B
 #endif
@@ -58,7 +61,7 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     // Small arrays (wavefront loops launch these by the thousand): up to four tiles are
     // walked by ONE CTA with the carry in registers -- no descriptor is read, so the memset launch
     // goes away as well (one launch in total; 2^14 u32: 7.4 -> ~6 us, the reference needs 6.2).
-    p.single_cta = !SEG && p.tiles > 1 && p.tiles <= 4;
+    p.single_cta = !SEG && STAGES == 0 && p.tiles > 1 && p.tiles <= 4;
     if (p.tiles > 1 && !p.single_cta)       // (a single tile never reads a descriptor)
         DJB_CUDA_CHECK(cudaMemsetAsync(p.state, 0, state_bytes, stream));
 

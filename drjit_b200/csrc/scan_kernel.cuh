@@ -204,6 +204,9 @@ prefix_reduce_kernel(const PrefixParams p) {
     constexpr bool STAGED = STAGES > 0;
     constexpr bool WINDOW = ScanRoles<SEG, STAGES>::WINDOW;
     constexpr uint32_t NS = STAGED ? STAGES : 1;
+    // (the one-CTA walk of small arrays is only ever launched on the unstaged instantiation: keep its
+    //  branches out of the TMA kernel)
+    constexpr bool SINGLE = !SEG && !STAGED;
     static_assert(!STAGED || VEC, "staged tiles need the 128-bit path");
     const A ident = Op::template identity<A>();
 
@@ -318,7 +321,7 @@ prefix_reduce_kernel(const PrefixParams p) {
 
     A carry = ident;            // WINDOW: reduction of everything before the current tile
     A prev_total = ident;       // single_cta: aggregate of the tile handled in the previous iteration
-    if (WINDOW || (!SEG && p.single_cta)) {
+    if (WINDOW || (SINGLE && p.single_cta)) {
         if (p.carry_in) carry = to_acc<A>(*(const T *) p.carry_in);
     }
 
@@ -346,7 +349,7 @@ prefix_reduce_kernel(const PrefixParams p) {
                 }
             }
         }
-        const uint32_t win_n = ((DJB_DEBUG(p.debug) & 1) || (!SEG && p.single_cta)) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
+        const uint32_t win_n = ((DJB_DEBUG(p.debug) & 1) || (SINGLE && p.single_cta)) ? 0u : tile - win_lo;   // (debug: carry chain disabled)
         if constexpr (WINDOW) {
             #pragma unroll
             for (uint32_t j = 0; j < kScanWindowLoads; ++j) {
@@ -520,13 +523,13 @@ prefix_reduce_kernel(const PrefixParams p) {
             #pragma unroll
             for (uint32_t w = 0; w < kScanWarps; ++w)
                 carry = Op::template apply<A>(carry, win_val[w]);
-            if (!SEG && p.single_cta && it > 0)             // one CTA: the previous tile was mine
+            if (SINGLE && p.single_cta && it > 0)           // one CTA: the previous tile was mine
                 carry = Op::template apply<A>(carry, prev_total);
             prev_total = tv;
             tile_carry = carry;
             if (!staged && tid == 0)     // (a ragged last tile was not published early; keeps the
                 state.publish(tile, kAggregate, tv);  //  descriptor array fully defined)
-        } else if (!SEG && p.single_cta) {
+        } else if (SINGLE && p.single_cta) {
             // one CTA walks all tiles in order: every thread knows the tile aggregate, the running
             // value stays in a register (no descriptor, no look-back, no extra barrier)
             tile_carry = carry;

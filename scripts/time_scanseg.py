@@ -34,7 +34,7 @@ def main():
                             ("f16", torch.float16, VarType.Float16, 1 << 29)):
         x = torch.rand(n, dtype=dt, device=dev) if dt.is_floating_point else torch.randint(0, 100, (n,), dtype=dt, device=dev)
         out = torch.empty_like(x)
-        for bs in (9, 12, 16, 20, 24, 28, 33, 40, 48, 64, 80, 100, 128, 160, 256, 1000, 4096, 32768 // x.element_size() * 4):
+        for bs in (9, 12, 16, 20, 24, 28, 33, 40, 48, 64, 80, 100, 128, 160, 256, 1000, 4096, 32768 // x.element_size() * 4, 100000, 1 << 20):
             for ex, rev in ((True, False),):
                 ms = timeit(lambda: ops.block_prefix_reduce(ReduceOp.Add, x, bs, ex, rev, vt=vt, out=out))
                 gbs = 2 * n * x.element_size() / ms / 1e6
