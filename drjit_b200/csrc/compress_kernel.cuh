@@ -273,8 +273,13 @@ compress_kernel(const CompressParams p) {
             uint32_t w = 0;
             #pragma unroll
             for (uint32_t j = 0; j < kCompWindowLoads; ++j) {
-                while ((uint32_t) wd[j] == kCInvalid) {     // a CTA that runs behind: poll
-                    __nanosleep(20);
+                // a CTA that runs behind: poll, backing off. On sparse masks an iteration is as short as a
+                // memory round trip and the grid advances in step with its slowest tile load: a third of
+                // all issued instructions were 20 ns polls (1 % density, profiles/r5g_ncu_compress01.md).
+                // They did not cost time (A/B: 0.381 against 0.379 ms, profiles/r5h_compress_poll_ab.txt)
+                // -- the issue slots were free -- but there is no reason to burn them.
+                for (uint32_t ns = 32; (uint32_t) wd[j] == kCInvalid; ns = ns < 256 ? ns * 2 : ns) {
+                    __nanosleep(ns);
                     wd[j] = ld_relaxed_u64(p.state + win_lo + j * kCompThreads + tid);
                 }
                 w += (uint32_t) (wd[j] >> 32);

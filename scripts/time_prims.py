@@ -148,6 +148,7 @@ def main():
     run("scanseg", 28, 8, s_scanseg)
     run("compress", 30, 3, s_compress(128))
     run("compress01", 30, 1 + 4 * 3 / 256, s_compress(3))
+    run("compress10", 30, 1 + 4 * 26 / 256, s_compress(26))
     run("compress99", 30, 1 + 4 * 253 / 256, s_compress(253))
     run("mkperm", 26, 12, s_mkperm(4096))
     run("mkperm256", 26, 12, s_mkperm(256))
