@@ -47,7 +47,9 @@ static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
 
     // outputs of at least twice the L2 size cannot stay resident anyway (smaller ones are left to the
     // default policy: a consumer kernel finds them in L2)
-    p.evict_first = (uint64_t) p.size * sizeof(T) >= ((uint64_t) 256 << 20);
+    // 4-byte types only, where it was measured to help (2^30 u32: 1.363 -> 1.345 ms). The 64-bit scan LOSES a
+    // quarter of its speed with these stores (2^28 u64: 0.983 -> 1.263 ms, profiles/r5j_scan_evict_first_ab.txt)
+    p.evict_first = sizeof(T) == 4 && (uint64_t) p.size * sizeof(T) >= ((uint64_t) 256 << 20);
 #if defined(DJB_AB_NO_EVICT_FIRST)
     p.evict_first = 0;          // (A/B build of the shipped configuration: make AB=... in csrc/Makefile)
 #endif
