@@ -618,7 +618,7 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
     for (uint32_t tile = first; tile < end; ++tile) {
         const uint64_t tile_base = (uint64_t) tile * TILE;
         const uint32_t n_tile = (uint32_t) min((uint64_t) TILE, (uint64_t) p.size - tile_base);
-        constexpr bool PACKED = KPT > kTileKeysPerThread;
+        constexpr bool PACKED = KPT != kTileKeysPerThread;  // (the unpacked loader is written for 32 keys per thread)
         uint32_t key[PACKED ? KPT / 2 : KPT];
         if constexpr (PACKED)
             tile_load_keys_packed<THREADS, KPT>(p, tile_base, n_tile, key);
@@ -645,11 +645,16 @@ mkperm_tile_hist_kernel(const MkpermTileParams p) {
     for (uint32_t b = tid; b < S; b += THREADS) row[b] = hist[b];
 }
 
-template <uint32_t THREADS, uint32_t KPT = kTileKeysPerThread>
+/// PAYS (jit_var_call_reduce with argument arrays, large inputs): the tile is half as large and the
+/// other half of shared memory holds the tile of ONE payload array at a time: coalesced 128-bit loads
+/// bring it in, the copy-out reads it at the staged local index (a shared-memory access instead of a
+/// scattered 4-byte global load per key: those ran at one 32-byte sector per lane and instruction,
+/// ~1.1 ms per array at 2^26 keys, as slow as a separate gather) and writes it where `perm` goes.
+template <uint32_t THREADS, uint32_t KPT = kTileKeysPerThread, bool PAYS = false>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 mkperm_tile_scatter_kernel(const MkpermTileParams p) {
     constexpr uint32_t TILE = THREADS * KPT, WARPS = THREADS / 32;
-    constexpr bool PACKED = KPT > kTileKeysPerThread;
+    constexpr bool PACKED = KPT != kTileKeysPerThread;
     static_assert(TILE <= 65536, "local indices are packed into 16 bits");
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t S = p.stride;
@@ -773,13 +778,36 @@ mkperm_tile_scatter_kernel(const MkpermTileParams p) {
 
         // ---- (3) runs of equal buckets are contiguous in `sorted` and in `perm` ----------------
         const uint32_t idx0 = p.index_base + (uint32_t) tile_base;
-        if (!(DJB_DEBUG(p.debug) & 15u) && p.n_pay) {
+        if (!(DJB_DEBUG(p.debug) & 15u) && p.n_pay && !PAYS) {
             tile_copy_out_payloads<THREADS>(p, sorted, delta, tile_base, n_tile, idx0);
         } else if (!(DJB_DEBUG(p.debug) & 15u)) {
             #pragma unroll 4
             for (uint32_t j = tid; j < n_tile; j += THREADS) {
                 const uint32_t e = sorted[j];
                 p.perm[delta[e >> 16] + j] = idx0 + (e & 0xffffu);
+            }
+            if constexpr (PAYS) {
+                uint32_t *pay_tile = sorted + TILE;         // [TILE] one payload array's values of this tile
+                for (uint32_t k = 0; k < p.n_pay; ++k) {
+                    const uint32_t *src = p.pay_in[k] + tile_base;
+                    uint32_t *dst = p.pay_out[k];
+                    if (n_tile == TILE && (((uintptr_t) src) & 15u) == 0) {
+                        #pragma unroll 4
+                        for (uint32_t i = tid; i < TILE / 4; i += THREADS) {
+                            const Vec16<uint32_t> t = ld_stream<uint32_t>(reinterpret_cast<const uint4 *>(src) + i);
+                            *reinterpret_cast<uint4 *>(pay_tile + 4 * i) = *reinterpret_cast<const uint4 *>(&t);
+                        }
+                    } else {
+                        for (uint32_t i = tid; i < n_tile; i += THREADS) pay_tile[i] = __ldg(src + i);
+                    }
+                    __syncthreads();
+                    #pragma unroll 4
+                    for (uint32_t j = tid; j < n_tile; j += THREADS) {
+                        const uint32_t e = sorted[j];
+                        dst[delta[e >> 16] + j] = pay_tile[e & 0xffffu];
+                    }
+                    __syncthreads();                        // the next array (or tile) overwrites pay_tile
+                }
             }
         } else if ((DJB_DEBUG(p.debug) & 15u) == 1u) {
             #pragma unroll 4
@@ -1418,7 +1446,7 @@ static void launch_stable_scatter(cudaStream_t stream, const MkpermTileParams &t
     mkperm_tile_scatter_stable_kernel<THREADS, KEY_BITS><<<grid, THREADS, smem, stream>>>(t);
 }
 
-template <uint32_t THREADS, bool STABLE, uint32_t KPT = kTileKeysPerThread>
+template <uint32_t THREADS, bool STABLE, uint32_t KPT = kTileKeysPerThread, bool PAYS = false>
 static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32_t size,
                              uint32_t bucket_count, uint32_t index_base, uint32_t *perm,
                              uint32_t *offsets, uint32_t *hist_out, const MkpermPeer *peer, const MkpermExtras &ex) {
@@ -1448,7 +1476,7 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
     const uint32_t hist_smem = t.stride * 8,
                    scatter_smem = STABLE ? (THREADS / 32 + 1) * t.stride * 4 + TILE * 4
                                 : STAGE16 ? t.stride * 10 + TILE / 32 * 6 + TILE * 2
-                                          : t.stride * 8 + TILE * 4;
+                                          : t.stride * 8 + TILE * 4 * (PAYS ? 2 : 1);
     uint32_t chunks = std::min(t.tiles, dev.sm_count * 2);
     t.tiles_per_chunk = ceil_div(t.tiles, chunks);
     chunks = ceil_div(t.tiles, t.tiles_per_chunk);
@@ -1497,8 +1525,8 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
         else
 #endif
         if (!STABLE)
-            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4, dev.smem_optin - 1024)));
+            DJB_CUDA_CHECK(cudaFuncSetAttribute(mkperm_tile_scatter_kernel<THREADS, KPT, PAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int) std::min<uint32_t>(kTileMaxBuckets * 8 + TILE * 4 * (PAYS ? 2 : 1), dev.smem_optin - 1024)));
         configured.store(true, std::memory_order_release);
     }
     if (!STABLE && scatter_smem > dev.smem_optin - 1024)
@@ -1556,7 +1584,7 @@ static uint32_t mkperm_tiles(cudaStream_t stream, const uint32_t *values, uint32
             mkperm_tile_scatter16_kernel<THREADS, KPT><<<std::min(t.tiles, dev.sm_count), THREADS, scatter_smem, stream>>>(t);
         else
 #endif
-            mkperm_tile_scatter_kernel<THREADS, KPT><<<grid, THREADS, scatter_smem, stream>>>(t);
+            mkperm_tile_scatter_kernel<THREADS, KPT, PAYS><<<grid, THREADS, scatter_smem, stream>>>(t);
     }
     DJB_POST_LAUNCH();
 
@@ -1650,6 +1678,17 @@ static uint32_t mkperm_impl(cudaStream_t stream, const uint32_t *values, uint32_
             size >= dev.sm_count * 2u * 1024u * 60u)
             return mkperm_tiles<1024, false, 60>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
 #endif
+        // Calls that carry payload arrays (jit_var_call_reduce): half of shared memory stages the payload
+        // tile, the key tile shrinks to 24 Ki (up to 4352 buckets) or 20 Ki keys (up to 8192)
+        if (ex.n_pay && !kpt_env) {
+            auto fits_pay = [&](uint32_t k) {
+                return stride * 8 + 2 * 1024 * k * 4 <= dev.smem_optin - 1024 && size >= dev.sm_count * 2u * 1024u * k;
+            };
+            if (fits_pay(24))
+                return mkperm_tiles<1024, false, 24, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
+            if (fits_pay(20))
+                return mkperm_tiles<1024, false, 20, true>(stream, values, size, bucket_count, index_base, perm, offsets, hist_out, peer, ex);
+        }
         // (two co-resident 512-thread CTAs with 20 Ki / 16 Ki-key tiles were measured and are slower:
         // 0.396 / 0.499 ms against 0.348 ms, profiles/r2o_mkperm_tile_keys.txt)
         if (kpt >= 48 && fits(48))

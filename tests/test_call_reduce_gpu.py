@@ -57,3 +57,26 @@ def test_call_reduce_without_payloads_matches_block_mkperm():
     assert outs == [] and torch.equal(perm, perm2)
     t2 = table2.numpy()
     assert np.array_equal(table.numpy(), t2[np.lexsort((t2[:, 0], -t2[:, 2]))])
+
+
+@pytest.mark.parametrize("buckets,npay", [(4096, 1), (4096, 4), (8000, 2)])
+def test_call_reduce_staged_payload_tiles(buckets, npay):
+    """Inputs large enough for the payload-staging tiles (24 Ki / 20 Ki keys, the payload tile in the
+    other half of shared memory): ragged last tile, one payload array deliberately not 16-byte
+    aligned (element-wise tile load), 1 .. 4 arrays, skewed IDs."""
+    n = 148 * 2 * 1024 * 24 + 12_345
+    keys = _keys(n, buckets, True)
+    pays = [capi.fmix32(n + 1, xor=11 + k) for k in range(npay)]
+    dev = [torch.from_numpy(x.view(np.int32)).cuda() for x in pays]
+    ins = [d[1:] if k == 0 else d[:n] for k, d in enumerate(dev)]         # payload 0 starts 4 bytes off alignment
+    perm, table, outs = dr.call_reduce(torch.from_numpy(keys.view(np.int32)).cuda(), buckets, ins)
+    torch.cuda.synchronize()
+    p = perm.cpu().numpy().view(np.uint32)
+    assert np.array_equal(np.sort(p), np.arange(n, dtype=np.uint32)) and np.all(np.diff(keys[p].astype(np.int64)) >= 0)
+    hist = np.bincount(keys, minlength=buckets)
+    rows = table.numpy()
+    assert rows.shape[0] == int((hist > 0).sum()) and np.all(np.diff(rows[:, 2]) <= 0)
+    assert np.array_equal(rows[:, 2], hist[rows[:, 0]])
+    for k, o in enumerate(outs):
+        src = pays[k][1:] if k == 0 else pays[k][:n]
+        assert np.array_equal(o.cpu().numpy().view(np.uint32), src[p]), k
