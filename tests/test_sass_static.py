@@ -19,7 +19,7 @@ SCAN = "_ZN3djb20prefix_reduce_kernelIjNS_5OpAddELb0ELb1ELj8ELj3ELj2EEEvNS_12Pre
 COMPRESS = "_ZN3djb15compress_kernelILj8ELj1ELj3ELj3ELb1ELb0EEEvNS_14CompressParamsE"
 SUM = "_ZN3djb25block_reduce_chunk_kernelIfNS_5OpAddELb0ELb1ELb0EEEvPKT_S4_PS2_PNS_3AccIS2_E4typeEPjjjjjNS_7PeerCtxEj"
 SUM_PEER = SUM.replace("ELb0ELb1ELb0EEE", "ELb0ELb1ELb1EEE")
-MKPERM_SCATTER = "_ZN3djb26mkperm_tile_scatter_kernelILj1024ELj%uEEEvNS_16MkpermTileParamsE"
+MKPERM_SCATTER = "_ZN3djb26mkperm_tile_scatter_kernelILj1024ELj%uELb0EEEvNS_16MkpermTileParamsE"
 MKPERM_HIST = "_ZN3djb23mkperm_tile_hist_kernelILj1024ELj48EEEvNS_16MkpermTileParamsE"
 MKPERM_STABLE = "_ZN3djb33mkperm_tile_scatter_stable_kernelILj1024ELj8EEEvNS_16MkpermTileParamsE"
 SCATTER = "_ZN3djb21scatter_reduce_kernelI%sNS_5Op%sELb0EEEvNS_13ScatterParamsE"
