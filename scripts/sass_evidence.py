@@ -19,11 +19,15 @@ LIB = os.path.join(ROOT, "drjit_b200", "lib", "libdrjit_b200.so")
 # demangled-name prefixes of the kernels the bench and the BASELINE configs run
 HOT = [
     "void djb::prefix_reduce_kernel<unsigned int, djb::OpAdd, false, true, 8u, 3u, 2u>",
-    "void djb::compress_kernel<8u, 1u, 3u>",
-    "void djb::mkperm_tile_scatter_kernel<1024u, 48u>",
+    "void djb::compress_kernel<8u, 1u, 3u, 3u, true, false>",
+    "void djb::compress_kernel<8u, 1u, 3u, 3u, true, true>",
+    "void djb::mkperm_tile_scatter_kernel<1024u, 48u, false>",
+    "void djb::mkperm_tile_scatter_kernel<1024u, 24u, true>",
     "void djb::mkperm_tile_scatter_stable_kernel<1024u, 8u>",
     "void djb::mkperm_tile_hist_kernel<1024u, 48u>",
-    "void djb::block_reduce_chunk_kernel<float, djb::OpAdd, false, true>",
+    "void djb::block_reduce_chunk_kernel<float, djb::OpAdd, false, true, false>",
+    "void djb::block_reduce_chunk_kernel<float, djb::OpAdd, false, true, true>",
+    "void djb::prefix_group_blocks_kernel<float, djb::OpAdd, 32u, false>",
     "void djb::block_reduce_group_kernel<float, djb::OpAdd, true, false>",
     "void djb::scatter_reduce_kernel<float, djb::OpAdd, false>",
 ]
