@@ -24,12 +24,12 @@ constexpr uint32_t kScanRows = 8, kScanStages = 3, kScanCtas = 2;
 // ---------------------------------------------------------------------------
 //  Host side
 // ---------------------------------------------------------------------------
-template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS, bool PEER = false>
+template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS>
 static void launch_prefix_geom(cudaStream_t stream, PrefixParams &p) {
     using A = acc_t<T>;
     using Geom = ScanGeom<T, VEC, R>;
     const DeviceProps &dev = device_props();
-    auto kernel = prefix_reduce_kernel<T, Op, SEG, VEC, R, STAGES, MIN_CTAS, PEER>;
+    auto kernel = prefix_reduce_kernel<T, Op, SEG, VEC, R, STAGES, MIN_CTAS>;
     constexpr uint32_t smem = STAGES * Geom::TILE_BYTES;
     constexpr uint32_t threads = ScanRoles<SEG, STAGES>::THREADS;
 
@@ -307,19 +307,6 @@ void comm_prefix_reduce(cudaStream_t stream, const Comm *comm, int vt, int op, u
     }
     if (!offset_out)
         raise(DRJIT_B200_EINVAL, "drjit_b200_comm_prefix_reduce(): the shard-offset form needs offset_out!");
-    // u32 / i32 sums of large aligned shards (dr.prefix_sum of indices and counts, the BASELINE config):
-    // the exchange runs INSIDE the scan kernel, in the thread that learns the shard's total -- no second
-    // launch, and the exchange overlaps the stores of the kernel's last tiles.
-    if ((vt == DRJIT_B200_VT_UINT32 || vt == DRJIT_B200_VT_INT32) && op == DRJIT_B200_OP_ADD &&
-        size > 4 * ScanGeom<uint32_t, true, kScanRows>::TILE && ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 &&
-        (!reverse || size % 4 == 0)) {
-        PrefixParams p{};
-        p.in = in; p.out = out; p.size = size; p.block_size = size;
-        p.exclusive = exclusive; p.reverse = reverse; p.in_place = in == out;
-        p.peer = comm_ctx(comm); p.offset_out = offset_out; p.fold = fold;
-        launch_prefix_geom<uint32_t, OpAdd, false, true, kScanRows, kScanStages, kScanCtas, true>(stream, p);
-        return;
-    }
     // u8 / f16 totals travel as 4-byte accumulators in the fused reduction; the scalar exchange
     // kernel handles the 4- and 8-byte types the scan totals of this form come in.
     void *total = scratch.device(256);

@@ -48,7 +48,6 @@
 
 #include "common.cuh"
 #include "tma.cuh"
-#include "comm.cuh"
 
 namespace djb {
 
@@ -122,12 +121,6 @@ struct PrefixParams {
     uint8_t single_cta;     // grid of one CTA walking all tiles in order: the carry stays in registers, the
                             // tile descriptors are neither read nor expected to be zero (no memset launch)
     uint8_t debug;          // read only in -DDRJIT_B200_EXPERIMENTS builds (scripts/sweep_scan.cu): 1 = skip look-back, 2 = skip stores
-    // PEER instantiations (shard of a global array, shard-offset form): the thread that learns the shard's
-    // total exchanges it through the communicator's scalar cells and writes the fold over the lower (reverse:
-    // higher) ranks to offset_out -- inside the scan kernel, while the other CTAs are still storing
-    PeerCtx peer;
-    void *offset_out;
-    uint32_t fold;
 };
 
 /// Tile geometry. A "unit" is what one thread moves at once (a 128-bit vector, or one element
@@ -200,7 +193,7 @@ __device__ __forceinline__ A scan_lookback(TileState<A> &state, uint32_t tile, u
     return excl;
 }
 
-template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS, bool PEER = false>
+template <typename T, typename Op, bool SEG, bool VEC, uint32_t R, uint32_t STAGES, uint32_t MIN_CTAS>
 __global__ void __launch_bounds__(kScanThreads, MIN_CTAS)
 prefix_reduce_kernel(const PrefixParams p) {
     using A = acc_t<T>;
@@ -566,12 +559,8 @@ prefix_reduce_kernel(const PrefixParams p) {
             scan_warps_sync();
             tile_carry = carry_smem;
         }
-        if ((PEER || p.total_out) && tile == p.tiles - 1 && tid == 0) {
-            const A total = tf ? tv : Op::template apply<A>(tile_carry, tv);
-            if (p.total_out) *(T *) p.total_out = from_acc<T>(total);
-            if constexpr (PEER)
-                *(T *) p.offset_out = from_acc<T>(peer_fold_scalar<Op, A>(p.peer, total, p.fold));
-        }
+        if (p.total_out && tile == p.tiles - 1 && tid == 0)
+            *(T *) p.total_out = from_acc<T>(tf ? tv : Op::template apply<A>(tile_carry, tv));
 
         // ---- combine and store -----------------------------------------------------
         const A warp_in = pf ? pv : Op::template apply<A>(tile_carry, pv);

@@ -18,8 +18,7 @@ LIB = os.path.join(ROOT, "drjit_b200", "lib", "libdrjit_b200.so")
 
 # demangled-name prefixes of the kernels the bench and the BASELINE configs run
 HOT = [
-    "void djb::prefix_reduce_kernel<unsigned int, djb::OpAdd, false, true, 8u, 3u, 2u, false>",
-    "void djb::prefix_reduce_kernel<unsigned int, djb::OpAdd, false, true, 8u, 3u, 2u, true>",
+    "void djb::prefix_reduce_kernel<unsigned int, djb::OpAdd, false, true, 8u, 3u, 2u>",
     "void djb::compress_kernel<8u, 1u, 3u, 3u, true, false>",
     "void djb::compress_kernel<8u, 1u, 3u, 3u, true, true>",
     "void djb::mkperm_tile_scatter_kernel<1024u, 48u, false>",
