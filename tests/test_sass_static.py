@@ -84,3 +84,14 @@ def test_scatter_reduce_uses_native_reductions():
         b = sass(SCATTER % ("6__half", op))
         assert re.search(rf"\bREDG?\.E\.{op.upper()}\.F16x2", b), f"f16 {op}: not a two-wide f16 reduction"
         assert not re.search(r"\bATOMG?\.E\.CAS", b), f"f16 {op}: compare-and-swap loop"
+
+
+def test_fused_compress_exchanges_inside_the_kernel():
+    """The PEER instantiation of the compaction publishes the shard's count to every rank from inside
+    the kernel (system-scope stores and loads of the scalar cells); the single-GPU one contains none."""
+    peer = COMPRESS.replace("ELb0EEEvNS_", "ELb1EEEvNS_")
+    assert peer != COMPRESS
+    b = sass(peer)
+    assert re.search(r"\bSTG?\.E\.\S*STRONG\.SYS", b), "no system-scope store"
+    assert re.search(r"\bLDG?\.E\.\S*STRONG\.SYS", b), "no system-scope load"
+    assert not re.search(r"\bSTG?\.E\.\S*STRONG\.SYS", sass(COMPRESS))
