@@ -242,6 +242,9 @@ void block_prefix_reduce(cudaStream_t stream, int vt, int op, uint32_t size, uin
         return;
     }
 
+    // Small arrays: one CTA, every load in flight at once (prefix_small.cu)
+    if (block_size == size && prefix_small(stream, vt, op, size, exclusive, reverse, in, out, carry_in, total_out))
+        return;
     // Medium blocks: a group of lanes per block (prefix_group.cu). Blocks of 2..8 elements of large
     // arrays stay with the thread-per-block kernel below (copy speed).
     if (block_size < size && !carry_in && !total_out && !(block_size <= 8 && size >= (1u << 16)) &&

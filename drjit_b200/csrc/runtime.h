@@ -143,6 +143,10 @@ void block_reduce(cudaStream_t s, int vt, int op, uint32_t size, uint32_t block_
 void block_reduce_bool(cudaStream_t s, const uint8_t *values, uint32_t size, uint8_t *out, int op);
 bool all_any(cudaStream_t s, const uint8_t *values, uint32_t size, int op);
 void reduce_dot(cudaStream_t s, int vt, const void *a, const void *b, uint32_t size, void *out);
+/// Unsegmented scan of a small array in one CTA with all loads in flight (prefix_small.cu); false if the
+/// configuration is left to the tile kernel
+bool prefix_small(cudaStream_t s, int vt, int op, uint32_t size, bool exclusive, bool reverse, const void *in,
+                  void *out, const void *carry_in, void *total_out);
 /// Segmented scan of medium-sized blocks by a group of lanes per block (prefix_group.cu); false if the
 /// configuration is left to the general kernel
 bool prefix_group_blocks(cudaStream_t s, int vt, int op, uint32_t size, uint32_t block_size, bool exclusive,

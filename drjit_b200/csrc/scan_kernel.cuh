@@ -531,9 +531,13 @@ prefix_reduce_kernel(const PrefixParams p) {
                 state.publish(tile, kAggregate, tv);  //  descriptor array fully defined)
         } else if (SINGLE && p.single_cta) {
             // one CTA walks all tiles in order: every thread knows the tile aggregate, the running
-            // value stays in a register (no descriptor, no look-back, no extra barrier)
+            // value stays in a register (no descriptor, no look-back)
             tile_carry = carry;
             carry = Op::template apply<A>(carry, tv);
+            // (the next tile rewrites warp_val / warp_flag: every warp must have read them. The unstaged
+            //  path has no other barrier between this read and that write -- racecheck found the hazard,
+            //  profiles/r5n_racecheck_single_cta.txt)
+            scan_warps_sync();
         } else {
             // decoupled look-back by warp 0 while the other warps wait
             if (warp == 0) {

@@ -354,6 +354,43 @@ def test_block_prefix_reduce_medium_blocks(vt):
         assert np.array_equal(to_np(y, vt), capi.block_prefix_reduce(vt, "max", x, bs, ex, rev)), ("in place", bs)
 
 
+@pytest.mark.parametrize("vt", ["u8", "f16", "u32", "i32", "f32", "u64", "f64"])
+def test_prefix_small_arrays_and_carry_form(vt):
+    """Arrays of up to 128 KiB take one 1024-thread CTA with all loads in flight (prefix_small.cu), larger
+    ones the tile kernel: sizes on both sides of every row / size limit, all four variants, in place, and
+    the carry form of sharded scans (carry_in / total_out) on both paths."""
+    item = np.dtype({"u8": np.uint8, "f16": np.float16, "u32": np.uint32, "i32": np.int32, "f32": np.float32,
+                     "u64": np.uint64, "f64": np.float64}[vt]).itemsize
+    V = 16 // item
+    sizes = [1, V - 1 if V > 1 else 1, V, V + 1, 1024 * V - 1, 1024 * V, 1024 * V + 1, 2 * 1024 * V + 5, 4 * 1024 * V,
+             8 * 1024 * V - 3, 8 * 1024 * V, 8 * 1024 * V + 1, 20 * 1024 * V + 7]
+    ops_for = ["add", "max"] + ([] if vt[0] == "f" else ["or"])
+    for size in sorted(set(sizes)):
+        x = make_input(vt, size); xd = to_dev(x, vt)
+        for op in ops_for:
+            for ex, rev in ((1, 0), (0, 0), (1, 1), (0, 1)):
+                got = to_np(dr.block_prefix_reduce(OPS[op], xd, size, ex, rev, vt=VT[vt]), vt)
+                exp = capi.block_prefix_reduce(vt, op, x, size, ex, rev, acc64=(vt[0] == "f"))
+                if vt[0] == "f" and op == "add":
+                    assert_close(got, exp, vt, size, f"{vt} prefix size={size}")
+                else:
+                    assert np.array_equal(got, exp), (vt, op, size, ex, rev)
+        y = xd.clone()
+        dr.block_prefix_reduce(OPS["max"], y, size, True, False, vt=VT[vt], out=y)
+        assert np.array_equal(to_np(y, vt), capi.block_prefix_reduce(vt, "max", x, size, 1, 0)), ("in place", size)
+    if vt in ("u32", "u64", "i32"):
+        # carry form: two pieces scanned one after the other == the scan of the whole (exact for integers)
+        for n, cut in ((5000, 1232), (5000, 1234), (3 * 8 * 1024 * V, 8 * 1024 * V - 4), (100_000 + 3, 70_001)):
+            x = make_input(vt, n); xd = to_dev(x, vt)
+            exp = capi.block_prefix_reduce(vt, "add", x, n, 1, 0)
+            out = torch.empty_like(xd)
+            carry = torch.zeros(1, dtype=xd.dtype, device="cuda"); total = torch.zeros(1, dtype=xd.dtype, device="cuda")
+            dr.ops.prefix_reduce_carry(OPS["add"], xd[:cut], True, False, carry_in=None, total_out=carry, vt=VT[vt], out=out[:cut])
+            dr.ops.prefix_reduce_carry(OPS["add"], xd[cut:], True, False, carry_in=carry, total_out=total, vt=VT[vt], out=out[cut:])
+            assert np.array_equal(to_np(out, vt), exp), (vt, n, cut)
+            assert to_np(total, vt)[0] == (x.astype(np.uint64).sum() & np.uint64((1 << (8 * item)) - 1)).astype(x.dtype), (vt, n)
+
+
 @pytest.mark.parametrize("vt", ["u8", "u32", "u64", "i32", "i64"])
 def test_prefix_windowed_carry_many_tiles(vt):
     """Unsegmented scans on the TMA path with more tiles than CTAs (every CTA advances its carry
