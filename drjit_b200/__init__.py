@@ -14,10 +14,12 @@ from .ops import (ReduceOp, ReduceMode, VarType, all, any, block_mkperm, block_p
                   block_prefix_sum, block_reduce, block_sum, compress, cumsum, dot, max, min,
                   prefix_sum, prod, scatter_add, scatter_reduce, sum, launch_count, version,
                   JitFlag, KernelType, set_flag, flag, kernel_history, kernel_history_clear,
-                  reserve_scratch, sort, argsort, sort_with_indices, call_reduce)
+                  reserve_scratch, sort, argsort, sort_with_indices, call_reduce,
+                  scatter_reduce_packet, scatter_inc)
 
 __all__ = ["ReduceOp", "ReduceMode", "VarType", "all", "any", "block_mkperm", "block_prefix_reduce",
            "block_prefix_sum", "block_reduce", "block_sum", "compress", "cumsum", "dot", "max",
            "min", "prefix_sum", "prod", "scatter_add", "scatter_reduce", "sum", "launch_count",
            "version", "JitFlag", "KernelType", "set_flag", "flag", "kernel_history",
-           "kernel_history_clear", "reserve_scratch", "sort", "argsort", "sort_with_indices", "call_reduce"]
+           "kernel_history_clear", "reserve_scratch", "sort", "argsort", "sort_with_indices", "call_reduce",
+           "scatter_reduce_packet", "scatter_inc"]

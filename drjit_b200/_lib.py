@@ -50,6 +50,8 @@ SIGNATURES = {
     "drjit_b200_poke": (i32, [vp, vp, vp, u32]),
     "drjit_b200_aggregate": (i32, [vp, vp, vp, u32]),
     "drjit_b200_scatter_reduce": (i32, [vp, i32, i32, i32, vp, u32, vp, vp, vp, u32]),
+    "drjit_b200_scatter_reduce_packet": (i32, [vp, i32, i32, i32, vp, u32, vp, u32, vp, vp, u32]),
+    "drjit_b200_scatter_inc": (i32, [vp, vp, u32, vp, vp, u32, vp]),
     "drjit_b200_prefix_reduce_carry": (i32, [vp, i32, i32, u32, i32, i32, vp, vp, vp, vp]),
     "drjit_b200_compress_async": (i32, [vp, vp, u32, u32, vp, vp]),
     "drjit_b200_mkperm_sharded": (i32, [vp, vp, u32, u32, u32, vp, vp]),

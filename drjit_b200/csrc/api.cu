@@ -168,6 +168,23 @@ DRJIT_B200_API int drjit_b200_scatter_reduce(void *stream, int vt, int op, int m
     });
 }
 
+DRJIT_B200_API int drjit_b200_scatter_reduce_packet(void *stream, int vt, int op, int mode, void *target,
+                                                    uint32_t target_packets, const void *const *values,
+                                                    uint32_t count, const uint32_t *index,
+                                                    const uint8_t *mask, uint32_t size) {
+    return primitive(DRJIT_B200_KT_SCATTER_REDUCE, size, stream, [&] {
+        djb::scatter_reduce_packet(S(stream), vt, op, mode, target, target_packets, values, count, index, mask, size);
+    });
+}
+
+DRJIT_B200_API int drjit_b200_scatter_inc(void *stream, uint32_t *target, uint32_t target_size,
+                                          const uint32_t *index, const uint8_t *mask, uint32_t size,
+                                          uint32_t *out) {
+    return primitive(DRJIT_B200_KT_SCATTER_REDUCE, size, stream, [&] {
+        djb::scatter_inc(S(stream), target, target_size, index, mask, size, out);
+    });
+}
+
 // ---- multi-GPU forms (comm.cu) ---------------------------------------------------------------
 #define COMM(c) ((djb::Comm *) (c))
 

@@ -168,6 +168,12 @@ void poke(cudaStream_t s, void *dst, const void *src, uint32_t size);
 void aggregate(cudaStream_t s, void *dst, const drjit_b200_aggregation_entry *agg, uint32_t size);
 void scatter_reduce(cudaStream_t s, int vt, int op, int mode, void *target, uint32_t target_size,
                     const void *value, const uint32_t *index, const uint8_t *mask, uint32_t size);
+/// Packet form of scatter_reduce and dr.scatter_inc (scatter_packet.cu)
+void scatter_reduce_packet(cudaStream_t s, int vt, int op, int mode, void *target, uint32_t target_packets,
+                           const void *const *values, uint32_t count, const uint32_t *index,
+                           const uint8_t *mask, uint32_t size);
+void scatter_inc(cudaStream_t s, uint32_t *target, uint32_t target_size, const uint32_t *index,
+                 const uint8_t *mask, uint32_t size, uint32_t *out);
 void fill_fmix32(cudaStream_t s, int kind, void *out, uint64_t start, uint64_t n, uint32_t xor_,
                  uint32_t and_);
 

@@ -6,7 +6,8 @@ tests read like the reference's own (citations relative to the reference tree):
   dr.block_reduce / dr.block_sum ......... src/python/reduce.cpp:704-740
   dr.block_prefix_reduce / prefix_sum .... src/python/reduce.cpp:742-769, drjit/_reduce.py:269-312
   dr.compress ............................ src/python/reduce.cpp:659-674
-  dr.scatter_reduce / scatter_add ........ src/python/memop.cpp:396-404
+  dr.scatter_reduce / scatter_add ........ src/python/memop.cpp:396-404 (ArrayNf values: packet form)
+  dr.scatter_inc ......................... src/python/memop.cpp:408-445 (jit_var_scatter_inc, jit.h:1126-1143)
   dr.detail.block_mkperm ................. src/python/detail.cpp:481-520
 Arrays are 1-D contiguous torch CUDA tensors; torch supplies device memory and the current
 stream only. Every function goes through the C ABI (``_lib``); there is no torch fallback.
@@ -384,7 +385,11 @@ def sort_with_indices(value, descending=False, vt=None):
 
 # --------------------------------------------------------------------------- scatter-reduce
 def scatter_reduce(op, target, value, index, active=None, mode=ReduceMode.Auto, vt=None):
-    """dr.scatter_reduce(op, target, value, index, active, mode): in-place on ``target``."""
+    """dr.scatter_reduce(op, target, value, index, active, mode): in-place on ``target``. A list / tuple
+    of component arrays as ``value`` is the packet form (``dr.scatter_reduce`` of an ArrayNf,
+    src/python/memop.cpp:396-404 -> jit_var_scatter_packet): see scatter_reduce_packet."""
+    if isinstance(value, (list, tuple)):
+        return scatter_reduce_packet(op, target, value, index, active, mode, vt)
     t = _check_array(target, "target"); val = _check_array(value, "value"); idx = _check_array(index, "index")
     if t.dtype != val.dtype:
         raise RuntimeError("drjit_b200: scatter_reduce(): target/value type mismatch")
@@ -403,6 +408,67 @@ def scatter_reduce(op, target, value, index, active=None, mode=ReduceMode.Auto, 
 
 def scatter_add(target, value, index, active=None, mode=ReduceMode.Auto):
     return scatter_reduce(ReduceOp.Add, target, value, index, active, mode)
+
+
+def _check_mask(active, n, what):
+    if active is None:
+        return None
+    m = _check_array(active, "active")
+    if m.dtype not in (torch.bool, torch.uint8) or m.numel() != n:
+        raise RuntimeError("drjit_b200: %s(): invalid mask" % what)
+    return m
+
+
+def scatter_reduce_packet(op, target, values, index, active=None, mode=ReduceMode.Auto, vt=None):
+    """Packet scatter-reduce (jit_var_scatter_packet, jit.h:1107-1120; PTX template
+    src/cuda_packet.cpp:168-327): ``target[index[i] * n + k] op= values[k][i]`` for the ``n`` component
+    arrays in ``values``; ``target`` is the flat array of packets. In-place on ``target``."""
+    t = _check_array(target, "target"); idx = _check_array(index, "index")
+    vals = [_check_array(v, "value") for v in values]
+    n = len(vals)
+    if n == 0 or builtins.any(v.dtype != t.dtype or v.numel() != idx.numel() for v in vals):
+        raise RuntimeError("drjit_b200: scatter_reduce_packet(): components must match the target's type "
+                           "and the index array's size")
+    if _vt(idx) not in (VarType.UInt32, VarType.Int32):
+        raise RuntimeError("drjit_b200: scatter_reduce_packet(): index must be a 32-bit integer array")
+    if t.numel() % n:
+        raise RuntimeError("drjit_b200: scatter_reduce_packet(): target size is not a multiple of the packet size")
+    m = _check_mask(active, idx.numel(), "scatter_reduce_packet")
+    ptrs = (ctypes.c_void_p * n)(*[_ptr(v) for v in vals])
+    with _on(t.device):
+        check(lib.drjit_b200_scatter_reduce_packet(_stream(t), _vt(t, vt), int(op), int(mode), _ptr(t),
+                                                   t.numel() // n, ptrs, n, _ptr(idx), _ptr(m), idx.numel()))
+    return target
+
+
+def scatter_inc(target, index=None, active=None, size=None, out=None):
+    """dr.scatter_inc(target, index, active) (src/python/memop.cpp:408-445 -> jit_var_scatter_inc, jit.h:1126-1143;
+    PTX template src/cuda_scatter.cpp:356-393): atomically ``out[i] = target[index[i]]++``; masked
+    elements receive 0. ``index=None`` with ``size`` (or a mask) is the queue form
+    ``dr.scatter_inc(counter, 0)``: every element increments ``target[0]``."""
+    t = _check_array(target, "target")
+    if _vt(t) not in (VarType.UInt32, VarType.Int32):
+        raise RuntimeError("drjit_b200: scatter_inc(): target must be a 32-bit integer array")
+    idx = None
+    if index is not None:
+        idx = _check_array(index, "index")
+        if _vt(idx) not in (VarType.UInt32, VarType.Int32):
+            raise RuntimeError("drjit_b200: scatter_inc(): index must be a 32-bit integer array")
+        n = idx.numel()
+    elif size is not None:
+        n = int(size)
+    elif active is not None:
+        n = active.numel()
+    else:
+        raise RuntimeError("drjit_b200: scatter_inc(): without an index array, pass size= or a mask")
+    m = _check_mask(active, n, "scatter_inc")
+    if out is None:
+        out = torch.empty(n, dtype=t.dtype, device=t.device)
+    elif out.numel() != n or out.dtype != t.dtype:
+        raise RuntimeError("drjit_b200: scatter_inc(): invalid output array")
+    with _on(t.device):
+        check(lib.drjit_b200_scatter_inc(_stream(t), _ptr(t), t.numel(), _ptr(idx), _ptr(m), n, _ptr(out)))
+    return out
 
 
 # --------------------------------------------------------------------------- misc

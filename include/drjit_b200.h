@@ -274,6 +274,35 @@ DRJIT_B200_API int drjit_b200_scatter_reduce(void *stream, int vt, int op, int m
                                              const uint32_t *index, const uint8_t *mask,
                                              uint32_t size);
 
+/* Packet form of the scatter-reduce template, jitc_cuda_render_scatter_reduce_packet(),
+ * src/cuda_packet.cpp:168-327 (jit_var_scatter_packet, jit.h:1107-1120; dr.scatter_reduce /
+ * dr.scatter_add of an ArrayNf, e.g. film accumulation):
+ *   target[index[i] * count + k] op= values[k][i]   for k < count, i < size where mask[i] != 0.
+ * `values` is a HOST array of `count` device pointers, one contiguous array of `size` elements per
+ * component (the layout of a Dr.Jit array of JIT arrays); `target` holds `target_packets` packets of
+ * `count` consecutive elements. `count` must be even (cuda_packet.cpp:184-186) and <= 16: EINVAL
+ * otherwise. (type, op) pairs as for drjit_b200_scatter_reduce. f32 Add and f16 Add/Min/Max leave as
+ * vector reductions of up to 16 bytes (red.global.v4.f32.add, red.global.v8.f16.<op>.noftz,
+ * cuda_packet.cpp:224-259) when `target` is aligned to the vector; all other pairs as one reduction
+ * per component. mode Local pre-combines lanes with equal index (not for f16, as in the reference,
+ * cuda_packet.cpp:200-207); Auto = Direct. */
+DRJIT_B200_API int drjit_b200_scatter_reduce_packet(void *stream, int vt, int op, int mode, void *target,
+                                                    uint32_t target_packets, const void *const *values,
+                                                    uint32_t count, const uint32_t *index,
+                                                    const uint8_t *mask, uint32_t size);
+
+/* Standalone form of jitc_cuda_render_scatter_inc(), src/cuda_scatter.cpp:356-393
+ * (jit_var_scatter_inc, jit.h:1126-1143; dr.scatter_inc): for every i < size with mask[i] != 0
+ * (mask may be NULL) atomically  out[i] = target[index[i]]++ ;  out[i] = 0 for masked elements
+ * (:361-364). `index` may be NULL: every element increments counter 0 (the queue form,
+ * dr.scatter_inc(counter, 0)). Which element receives which of the slots handed out for one counter is
+ * unspecified (the reference aggregates per warp, here small counter arrays are aggregated per CTA);
+ * the slots of a counter are distinct and contiguous from its value before the call. Indices
+ * >= target_size (undefined behaviour in the reference) are ignored and yield 0. */
+DRJIT_B200_API int drjit_b200_scatter_inc(void *stream, uint32_t *target, uint32_t target_size,
+                                          const uint32_t *index, const uint8_t *mask, uint32_t size,
+                                          uint32_t *out);
+
 /* jit_var_call_reduce, src/call.cpp:1268-1389 (dr.dispatch / vcall reordering), as one call:
  * block_mkperm of the callable IDs with block_size == size, plus
  *  - the table of non-empty buckets already in the order the dispatcher uses -- decreasing bucket

@@ -48,6 +48,7 @@ def lib():
         L.oracle_all.argtypes = [vp, u32]
         L.oracle_any.argtypes = [vp, u32]
         L.oracle_scatter_reduce.argtypes = [i32, i32, vp, u32, vp, vp, vp, u32, i32]
+        L.oracle_scatter_inc.argtypes = [vp, u32, vp, vp, u32, vp]
         L.oracle_memset.argtypes = [vp, u32, u32, vp]
         L.oracle_scatter_add_expand_f32.argtypes = [vp, u32, vp, vp, u32, u32, vp]
         L.oracle_aggregate.argtypes = [vp, vp, u32]
@@ -160,6 +161,31 @@ def scatter_reduce(vt, op, target, value, index, mask=None, acc64=False):
     _check(lib().oracle_scatter_reduce(VT[vt], OP[op], _p(target), target.size, _p(value), _p(index),
                                        _p(m), value.size, int(acc64)), "scatter_reduce")
     return target
+
+
+def scatter_reduce_packet(vt, op, target, values, index, mask=None, acc64=False):
+    """Packet scatter-reduce, target[index[i] * n + k] op= values[k][i] (jit_var_scatter_packet,
+    jit.h:1107-1120: "analogous to n separate scatters from indices index*n + [0, 1, .., n-1]";
+    CUDA template src/cuda_packet.cpp:168-327). Restated exactly as that sentence: the n component
+    scatters run through the scalar restatement above, serial in element order."""
+    n = len(values)
+    index = np.ascontiguousarray(index, np.uint32)
+    flat_index = (index.astype(np.uint64)[:, None] * n + np.arange(n, dtype=np.uint64)[None, :]).reshape(-1)
+    assert flat_index.size == 0 or int(flat_index.max()) < 2 ** 32
+    flat_value = np.ascontiguousarray(np.stack([np.asarray(v, NP[vt]) for v in values], axis=1)).reshape(-1)
+    flat_mask = np.repeat(np.ascontiguousarray(mask, np.uint8), n) if mask is not None else None
+    return scatter_reduce(vt, op, target, flat_value, flat_index.astype(np.uint32), flat_mask, acc64)
+
+
+def scatter_inc(target, index, mask=None, size=None):
+    """dr.scatter_inc in serial element order: returns (target_after, out). index=None: counter 0."""
+    target = np.array(target, np.uint32, copy=True)
+    idx = np.ascontiguousarray(index, np.uint32) if index is not None else None
+    n = idx.size if idx is not None else (int(size) if size is not None else np.asarray(mask).size)
+    m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+    out = np.empty(n, np.uint32)
+    _check(lib().oracle_scatter_inc(_p(target), target.size, _p(idx), _p(m), n, _p(out)), "scatter_inc")
+    return target, out
 
 
 def scatter_add_expand_f32(target, value, index, workers, scratch=None):

@@ -432,6 +432,23 @@ EXPORT int oracle_scatter_reduce(int vt, int op, void *target, uint32_t target_s
     }
 }
 
+/* scatter_inc: out[i] = target[index[i]]++, serial in index order (jit_var_scatter_inc, jit.h:1126-1143;
+ * CUDA template src/cuda_scatter.cpp:356-393: masked lanes return 0, :361-364). index == NULL: every
+ * element increments counter 0. The GPU assigns the slots of a counter in an unspecified order, so this
+ * serial order is ONE valid result; tests compare the counters exactly and the slots per counter as sets
+ * (the property the reference's own test checks, tests/test_memop.py:293-316). */
+EXPORT int oracle_scatter_inc(uint32_t *target, uint32_t target_size, const uint32_t *index,
+                              const uint8_t *mask, uint32_t size, uint32_t *out) {
+    for (uint32_t i = 0; i < size; ++i) {
+        out[i] = 0;
+        if (mask && !mask[i]) continue;
+        uint32_t k = index ? index[i] : 0;
+        if (k >= target_size) return -3;
+        out[i] = target[k]++;
+    }
+    return 0;
+}
+
 /* scatter_add in ReduceMode::Expand, the mode the reference's LLVM backend picks for targets of
  * up to 1 M entries (src/op.cpp:2845-2848, src/api.cpp:2073): the target is replicated once per
  * worker (jitc_var_expand, src/var.cpp:2866-2931; replication factor = pool size,

@@ -53,6 +53,9 @@ def lib(cuda=False, llvm=True):
         if hasattr(L, "ref_scatter_reduce_masked"):
             L.ref_scatter_reduce_masked.argtypes = [i32, i32, i32, i32, vp, u32, vp, vp, vp, u32]
             L.ref_kernel_history_ir_count.argtypes = [ctypes.c_char_p]; L.ref_kernel_history_ir_count.restype = u32
+        if hasattr(L, "ref_scatter_packet"):
+            L.ref_scatter_packet.argtypes = [i32, i32, i32, i32, vp, u32, ctypes.POINTER(vp), u32, vp, vp, u32]
+            L.ref_scatter_inc.argtypes = [i32, vp, u32, vp, vp, u32, vp]
         _lib = L
     want = (2 if cuda else 0) | (4 if llvm else 0)
     if want & ~_backends:

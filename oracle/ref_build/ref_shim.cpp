@@ -162,6 +162,55 @@ SHIM int ref_scatter_reduce_masked(int backend, int vt, int op, int mode, void *
     });
 }
 
+/// dr.scatter_reduce of an n-component packet through the reference tracer (jit_var_scatter_packet,
+/// jit.h:1117-1120; PTX from cuda_packet.cpp:168-327). `values` = host array of n device pointers,
+/// `target` = target_packets * n elements; mask (u8 device array) may be NULL.
+SHIM int ref_scatter_packet(int backend, int vt, int op, int mode, void *target, uint32_t target_packets,
+                            void **values, uint32_t n, void *index, void *mask, uint32_t size) {
+    return guard([&] {
+        JitBackend be = (JitBackend) backend;
+        const size_t tsize = vt == (int) VarType::Float64 || vt == (int) VarType::UInt64 || vt == (int) VarType::Int64 ? 8
+                           : vt == (int) VarType::Float16 ? 2 : 4;
+        uint32_t vt_ = jit_var_mem_map(be, (VarType) vt, target, (size_t) target_packets * n, 0),
+                 vi  = jit_var_mem_map(be, VarType::UInt32, index, size, 0),
+                 vm  = mask ? jit_var_mem_map(be, VarType::Bool, mask, size, 0) : jit_var_bool(be, true);
+        uint32_t vv[16];
+        for (uint32_t k = 0; k < n; ++k)
+            vv[k] = jit_var_mem_map(be, (VarType) vt, values[k], size, 0);
+        uint32_t vr = jit_var_scatter_packet(n, vt_, vv, vi, vm, (ReduceOp) op, (ReduceMode) mode);
+        jit_var_eval(vr);
+        void *p = nullptr;
+        jit_var_data(vr, &p);
+        if (p != target)
+            jit_memcpy_async(be, target, p, (size_t) target_packets * n * tsize);
+        jit_var_dec_ref(vr); jit_var_dec_ref(vi); jit_var_dec_ref(vm);
+        for (uint32_t k = 0; k < n; ++k) jit_var_dec_ref(vv[k]);
+    });
+}
+
+/// dr.scatter_inc through the reference tracer (jit_var_scatter_inc, jit.h:1141-1143; PTX from
+/// cuda_scatter.cpp:356-393): out[i] = target[index[i]]++. All device pointers; mask may be NULL.
+SHIM int ref_scatter_inc(int backend, void *target, uint32_t target_size, void *index, void *mask,
+                         uint32_t size, void *out) {
+    return guard([&] {
+        JitBackend be = (JitBackend) backend;
+        uint32_t vt_ = jit_var_mem_map(be, VarType::UInt32, target, target_size, 0),
+                 vi  = jit_var_mem_map(be, VarType::UInt32, index, size, 0),
+                 vm  = mask ? jit_var_mem_map(be, VarType::Bool, mask, size, 0) : jit_var_bool(be, true);
+        uint32_t vr = jit_var_scatter_inc(&vt_, vi, vm);
+        jit_var_eval(vr);
+        void *p = nullptr;
+        jit_var_data(vr, &p);
+        jit_memcpy_async(be, out, p, (size_t) size * 4);
+        void *pt = nullptr;
+        jit_var_data(vt_, &pt);
+        if (pt != target)
+            jit_memcpy_async(be, target, pt, (size_t) target_size * 4);
+        jit_sync_thread();
+        jit_var_dec_ref(vr); jit_var_dec_ref(vt_); jit_var_dec_ref(vi); jit_var_dec_ref(vm);
+    });
+}
+
 /// Number of kernel-history entries whose IR (the PTX the JIT generated) contains `needle`;
 /// consumes the history like ref_kernel_history.
 SHIM uint32_t ref_kernel_history_ir_count(const char *needle) {

@@ -3,7 +3,7 @@
 
     python scripts/time_prims.py [prim ...] [--log2 N] [--reps R]
 prims: sum block_reduce dot scan scan64 scanseg compress compress01 compress99 mkperm mkperm256 scatter sort sortkeys
-       sort_composed torch_sort (the last two only when named) all
+       packet scatter_inc sort_composed torch_sort (the last two only when named) all
 """
 import argparse
 import os
@@ -55,8 +55,8 @@ def main():
     want = set(a.prims)
     dev = "cuda"
 
-    def run(name, log2, bytes_per_elem, setup):
-        if "all" not in want and name not in want:
+    def run(name, log2, bytes_per_elem, setup, group=None):
+        if "all" not in want and name not in want and group not in want:
             return
         n = 1 << (a.log2 or log2)
         fn = setup(n)
@@ -178,6 +178,44 @@ def main():
         run("call_reduce", 26, 12 + 2 * 8, s_call_reduce_unfused)
     run("sort", 26, 4 * 20 + 0, s_sort(True))          # key + index: 20 B per element and pass
     run("sortkeys", 26, 4 * 12, s_sort(False))
+    # ---- scatter_packet.cu: packet scatter-add (film accumulation) and scatter_inc ------------------------
+    def s_packet(count, log2_packets, four_scalar=False):
+        def setup(n):
+            vals = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(count)]
+            for k, v in enumerate(vals):
+                ops.fill_fmix32(v, 1, xor=k + 1)
+            i = torch.empty(n, dtype=torch.int32, device=dev)
+            ops.fill_fmix32(i, 0, xor=0x85EBCA6B, and_=(1 << log2_packets) - 1)
+            tgt = torch.zeros(count << log2_packets, dtype=torch.float32, device=dev)
+            if not four_scalar:
+                return lambda: dr.scatter_add(tgt, vals, i)
+            # what a caller without the packet form does: one scalar scatter per component at index * count + k
+            idxs = [(i * count + k) for k in range(count)]
+            return lambda: [dr.scatter_add(tgt, vals[k], idxs[k]) for k in range(count)]
+        return setup
+
+    def s_inc(log2_counters, queue=False):
+        def setup(n):
+            B = 1 << log2_counters
+            tgt = torch.zeros(B, dtype=torch.int32, device=dev)
+            out = torch.empty(n, dtype=torch.int32, device=dev)
+            if queue:
+                return lambda: ops.scatter_inc(tgt, None, size=n, out=out)
+            i = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(i, 0, xor=7, and_=B - 1)
+            return lambda: ops.scatter_inc(tgt, i, out=out)
+        return setup
+
+    if want & {"packet", "scatter_inc", "all"}:
+        if want & {"packet", "all"}:
+            run("packet4", 26, 20, s_packet(4, 20), group="packet")                      # 2^26 RGBA samples -> 2^20 pixels
+            run("packet4x1", 26, 32, s_packet(4, 20, four_scalar=True), group="packet")  # the same as four scalar scatters
+            run("packet2", 26, 12, s_packet(2, 20), group="packet")
+            run("packet8", 26, 36, s_packet(8, 20), group="packet")
+        if want & {"scatter_inc", "all"}:
+            run("inc_queue", 28, 4, s_inc(0, queue=True), group="scatter_inc")                # one counter, no index array
+            run("inc_16", 28, 8, s_inc(4), group="scatter_inc")
+            run("inc_2048", 28, 8, s_inc(11), group="scatter_inc")
+            run("inc_2^20", 26, 8, s_inc(20), group="scatter_inc")
     if "sort_composed" in want:
         run("sort_composed", 26, 4 * 20, s_sort_composed)
     if "torch_sort" in want:

@@ -95,3 +95,26 @@ def test_fused_compress_exchanges_inside_the_kernel():
     assert re.search(r"\bSTG?\.E\.\S*STRONG\.SYS", b), "no system-scope store"
     assert re.search(r"\bLDG?\.E\.\S*STRONG\.SYS", b), "no system-scope load"
     assert not re.search(r"\bSTG?\.E\.\S*STRONG\.SYS", sass(COMPRESS))
+
+
+PACKET = "_ZN3djb21scatter_packet_kernelI%sNS_5Op%sELj%uELb%uEEEvNS_12PacketParamsE"
+
+
+def test_packet_scatter_uses_vector_reductions():
+    """scatter_packet.cu: a whole packet (or 16 bytes of it) per reduction instruction
+    (red.global.v4.f32.add / red.global.v8.f16.<op>.noftz, cuda_packet.cpp:224-259)"""
+    assert re.search(r"\bREDG\.E\.ADD\.F32x4", sass(PACKET % ("f", "Add", 4, 0)))
+    assert re.search(r"\bREDG\.E\.ADD\.F32x2", sass(PACKET % ("f", "Add", 2, 0)))
+    assert re.search(r"\bREDG\.E\.MAX\.F16x8", sass(PACKET % ("6__half", "Max", 8, 0)))
+    assert re.search(r"\bREDG\.E\.ADD\.F16x4", sass(PACKET % ("6__half", "Add", 4, 0)))
+    local = sass(PACKET % ("f", "Add", 4, 1))
+    assert re.search(r"\bMATCH\.ANY", local) and re.search(r"\bREDG\.E\.ADD\.F32x4", local)
+
+
+def test_scatter_inc_aggregates_per_cta():
+    """small counter arrays: shared-memory atomics with return + one global atomic per touched counter
+    and tile; coherent warps are detected with one vote (match.all)"""
+    b = sass("_ZN3djb26scatter_inc_private_kernelENS_9IncParamsE")
+    assert re.search(r"\bATOMS\.ADD", b) and re.search(r"\bMATCH\.ALL", b) and re.search(r"\bATOMG\.E\.ADD", b)
+    g = sass("_ZN3djb18scatter_inc_kernelENS_9IncParamsE")
+    assert re.search(r"\bMATCH\.ANY", g) and re.search(r"\bATOMG\.E\.ADD", g)
