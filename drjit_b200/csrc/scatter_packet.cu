@@ -19,7 +19,9 @@
  *    ONE shared-memory atomic), one global atomic per touched counter and tile fetches the base, and
  *    the slots are base + tile-local rank. A single queue counter then sees size / 2048 global atomics
  *    instead of size / 32 on one address (the L2 retires ~1.4 G same-address atomics per second:
- *    DESIGN.md 4.10). Larger counter arrays take the warp-aggregated form.
+ *    DESIGN.md 4.10). Larger counter arrays take the warp-aggregated form. The queue form (no index
+ *    array: every active element takes a slot from counter 0) needs no per-element atomic at all: mask
+ *    bits, popc, one scan and one global atomic per 8192-element tile (scatter_inc_queue_kernel).
  *    Which lane receives which slot is unspecified in the reference as well; the slots of one counter
  *    are distinct and contiguous from its previous value (tests/test_memop.py:293-316).
  */
@@ -151,6 +153,64 @@ scatter_packet_kernel(const PacketParams p) {
     }
 }
 
+/// Fast path of the common case -- Direct mode, 4-byte components, COUNT known at compile time, every
+/// array 16-byte aligned: a thread owns four consecutive elements, i.e. one 128-bit load of the indices
+/// and one per component (a quarter of the load instructions of the kernel above, no parameter-space
+/// indexing), then four packet reductions; the 4 x COUNT register transpose is free.
+template <typename T, typename Op, uint32_t COUNT, uint32_t W>
+__global__ void __launch_bounds__(kPkThreads)
+scatter_packet_vec_kernel(const PacketParams p) {
+    static_assert(sizeof(T) == 4 && COUNT % W == 0, "four elements per 128-bit load");
+    T *target = (T *) p.target;
+    const uint64_t gtid = (uint64_t) blockIdx.x * kPkThreads + threadIdx.x,
+                   gstride = (uint64_t) gridDim.x * kPkThreads;
+    const uint64_t ngroups = p.size / 4;
+    for (uint64_t g = gtid; g < ngroups; g += gstride) {
+        const Vec16<uint32_t> iv = ld_stream<uint32_t>(p.index + g * 4);
+        Vec16<T> vv[COUNT];
+        #pragma unroll
+        for (uint32_t k = 0; k < COUNT; ++k)
+            vv[k] = ld_stream<T>((const T *) p.values[k] + g * 4);
+        const uint32_t m = p.mask ? *reinterpret_cast<const uint32_t *>(p.mask + g * 4) : 0x01010101u;
+        #pragma unroll
+        for (uint32_t e = 0; e < 4; ++e) {
+            if (((m >> (8 * e)) & 0xffu) == 0)
+                continue;
+            T *dst = target + (uint64_t) iv.v[e] * COUNT;
+            #pragma unroll
+            for (uint32_t c = 0; c < COUNT; c += W) {
+                T v[W];
+                #pragma unroll
+                for (uint32_t k = 0; k < W; ++k) v[k] = vv[c + k].v[e];
+                PacketRed<Op, T, W>::apply(dst + c, v);
+            }
+        }
+    }
+    const uint64_t tail = ngroups * 4;
+    if (gtid < p.size - tail) {
+        const uint64_t i = tail + gtid;
+        if (!p.mask || p.mask[i]) {
+            T *dst = target + (uint64_t) p.index[i] * COUNT;
+            #pragma unroll
+            for (uint32_t c = 0; c < COUNT; c += W) {
+                T v[W];
+                #pragma unroll
+                for (uint32_t k = 0; k < W; ++k) v[k] = ((const T *) p.values[c + k])[i];
+                PacketRed<Op, T, W>::apply(dst + c, v);
+            }
+        }
+    }
+}
+
+template <typename T, typename Op, uint32_t COUNT, uint32_t W>
+static void launch_packet_vec(cudaStream_t stream, const PacketParams &p) {
+    const DeviceProps &dev = device_props();
+    uint32_t grid = (uint32_t) std::min<uint64_t>(ceil_div64(p.size, kPkThreads * 4 * 2), (uint64_t) dev.sm_count * 8 * 4);
+    grid = std::max(grid, 1u);
+    scatter_packet_vec_kernel<T, Op, COUNT, W><<<grid, kPkThreads, 0, stream>>>(p);
+    DJB_POST_LAUNCH();
+}
+
 template <typename T, typename Op, uint32_t W, bool LOCAL>
 static void launch_packet_w(cudaStream_t stream, const PacketParams &p) {
     const DeviceProps &dev = device_props();
@@ -166,6 +226,14 @@ template <typename T, typename Op, bool LOCAL>
 static void launch_packet(cudaStream_t stream, const PacketParams &p) {
     constexpr bool f32_add = std::is_same<T, float>::value && std::is_same<Op, OpAdd>::value;
     constexpr bool f16 = std::is_same<T, __half>::value;
+    if constexpr (f32_add && !LOCAL) {
+        bool aligned = ((uintptr_t) p.target % 16) == 0 && ((uintptr_t) p.index % 16) == 0 &&
+                       (!p.mask || ((uintptr_t) p.mask % 4) == 0);
+        for (uint32_t k = 0; k < p.count; ++k) aligned = aligned && ((uintptr_t) p.values[k] % 16) == 0;
+        if (aligned && p.count == 2) return launch_packet_vec<T, Op, 2, 2>(stream, p);
+        if (aligned && p.count == 4) return launch_packet_vec<T, Op, 4, 4>(stream, p);
+        if (aligned && p.count == 8) return launch_packet_vec<T, Op, 8, 4>(stream, p);
+    }
     if constexpr (f32_add || f16) {
         uint32_t w = 16 / sizeof(T);
         while (w > 1 && ((p.count & (w - 1)) != 0 || ((uintptr_t) p.target % (w * sizeof(T))) != 0))
@@ -276,9 +344,10 @@ scatter_inc_private_kernel(const IncParams p) {
     __syncthreads();
 
     const uint64_t tiles = ((uint64_t) p.size + kIncTile - 1) / kIncTile;
-    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    // indices + activity bits of one tile -> registers
+    auto fetch = [&](uint64_t t, uint32_t (&idx)[kIncPerThread], uint32_t &okbits) {
         const uint64_t base = t * kIncTile;
-        uint32_t idx[kIncPerThread], loc[kIncPerThread], okbits = 0;
+        okbits = 0;
         #pragma unroll
         for (uint32_t j = 0; j < kIncPerThread; ++j) {
             const uint64_t i = base + (uint64_t) j * kIncThreads + tid;
@@ -287,6 +356,19 @@ scatter_inc_private_kernel(const IncParams p) {
             ok = ok && idx[j] < B;                  // (out-of-range counters: ignored, slot 0)
             okbits |= (uint32_t) ok << j;
         }
+    };
+    // The next tile's loads are issued before this tile's barriers and stores: issued after them they
+    // queue behind the stores of the other CTAs of the SM and the tile waits for the drain
+    // (profiles/r6b_ncu_scatter_packet.md: long_scoreboard).
+    uint32_t idx_n[kIncPerThread], okbits_n = 0;
+    if (blockIdx.x < tiles) fetch(blockIdx.x, idx_n, okbits_n);
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint64_t base = t * kIncTile;
+        uint32_t idx[kIncPerThread], loc[kIncPerThread];
+        const uint32_t okbits = okbits_n;
+        #pragma unroll
+        for (uint32_t j = 0; j < kIncPerThread; ++j) idx[j] = idx_n[j];
+        if (t + gridDim.x < tiles) fetch(t + gridDim.x, idx_n, okbits_n);
         #pragma unroll
         for (uint32_t j = 0; j < kIncPerThread; ++j) {
             const bool ok = (okbits >> j) & 1u;
@@ -325,6 +407,100 @@ scatter_inc_private_kernel(const IncParams p) {
     }
 }
 
+/// Queue form (index == NULL: every active element takes a slot from counter 0, dr.scatter_inc(queue, 0,
+/// active) -- the stream-compaction use the reference names, jit.h:1137-1138). No per-element atomics at
+/// all: a tile of 8192 elements counts its active elements (mask bytes -> bits, popc), one shuffle scan +
+/// an 8-entry combine rank them, ONE global atomic per tile fetches the base. A lane owns four consecutive
+/// elements per round, so the mask arrives as coalesced 32-bit loads and the slots leave as coalesced
+/// 128-bit stores. Two barriers per tile; the per-warp sums and the base are double-buffered so that a
+/// fast warp may enter the next tile while a slow one still reads this tile's.
+constexpr uint32_t kQueueRounds = 8;
+constexpr uint32_t kQueueTile = kIncThreads * 4 * kQueueRounds;
+
+__global__ void __launch_bounds__(kIncThreads)
+scatter_inc_queue_kernel(const IncParams p) {
+    __shared__ uint32_t wsum[2][kIncThreads / 32], sbase[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool vec = ((uintptr_t) p.out % 16) == 0 && (!p.mask || ((uintptr_t) p.mask % 4) == 0);
+    const uint64_t size = p.size, tiles = (size + kQueueTile - 1) / kQueueTile;
+    // mask bytes of the lane's 8 x 4 elements of one tile, one 32-bit word per round
+    auto fetch = [&](uint64_t t, uint32_t (&m)[kQueueRounds]) {
+        const uint64_t base = t * kQueueTile;
+        #pragma unroll
+        for (uint32_t r = 0; r < kQueueRounds; ++r) {
+            const uint64_t e0 = base + (uint64_t) (r * kIncThreads + tid) * 4;
+            uint32_t m4 = 0;
+            if (vec && e0 + 4 <= size) {
+                m4 = p.mask ? *reinterpret_cast<const uint32_t *>(p.mask + e0) : 0x01010101u;
+            } else {
+                #pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (e0 + k < size && (!p.mask || p.mask[e0 + k]))
+                        m4 |= 1u << (8 * k);
+            }
+            m[r] = m4;
+        }
+    };
+    uint32_t par = 0, m_n[kQueueRounds];
+    if (blockIdx.x < tiles) fetch(blockIdx.x, m_n);
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x, par ^= 1u) {
+        const uint64_t base = t * kQueueTile;
+        uint32_t bits = 0;                  // four bits per round: which of the lane's elements are active
+        #pragma unroll
+        for (uint32_t r = 0; r < kQueueRounds; ++r) {
+            const uint32_t m4 = m_n[r];
+            const uint32_t nz = (((m4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m4) & 0x80808080u;    // bit 7 of each non-zero byte
+            const uint32_t b4 = ((nz >> 7) & 1u) | ((nz >> 14) & 2u) | ((nz >> 21) & 4u) | ((nz >> 28) & 8u);
+            bits |= b4 << (4 * r);
+        }
+        // the next tile's mask words travel while this tile is ranked and stored (loads issued after the
+        // stores queue behind those of the SM's other CTAs: profiles/r6b_ncu_scatter_packet.md)
+        if (p.mask && t + gridDim.x < tiles) fetch(t + gridDim.x, m_n);
+        const uint32_t count = __popc(bits);
+        uint32_t incl = count;
+        #pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t o = shfl_up(incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) wsum[par][warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t total = 0;
+            #pragma unroll
+            for (uint32_t w = 0; w < kIncThreads / 32; ++w) total += wsum[par][w];
+            sbase[par] = total ? atomicAdd(p.target, total) : 0u;
+        }
+        __syncthreads();
+        uint32_t off = sbase[par] + incl - count;
+        #pragma unroll
+        for (uint32_t w = 0; w < kIncThreads / 32; ++w)
+            if (w < warp) off += wsum[par][w];
+        #pragma unroll
+        for (uint32_t r = 0; r < kQueueRounds; ++r) {
+            const uint64_t e0 = base + (uint64_t) (r * kIncThreads + tid) * 4;
+            const uint32_t b4 = (bits >> (4 * r)) & 15u;
+            uint32_t slot[4];
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t on = (b4 >> k) & 1u;
+                slot[k] = on ? off : 0u;
+                off += on;
+            }
+            if (vec && e0 + 4 <= size) {
+                Vec16<uint32_t> v;
+                #pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) v.v[k] = slot[k];
+                st_stream<uint32_t>(p.out + e0, v);
+            } else {
+                #pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (e0 + k < size) p.out[e0 + k] = slot[k];
+            }
+        }
+    }
+}
+
 /// Any counter array: the reference's warp-aggregated form (cuda_scatter.cpp:370-388)
 __global__ void __launch_bounds__(kIncThreads)
 scatter_inc_kernel(const IncParams p) {
@@ -360,7 +536,10 @@ void scatter_inc(cudaStream_t stream, uint32_t *target, uint32_t target_size, co
     const DeviceProps &dev = device_props();
     IncParams p{};
     p.target = target; p.index = index; p.mask = mask; p.out = out; p.size = size; p.target_size = target_size;
-    if (target_size <= kIncPrivMax) {
+    if (!index) {
+        const uint32_t grid = (uint32_t) std::min<uint64_t>(ceil_div64(size, kQueueTile), (uint64_t) dev.sm_count * 8);
+        scatter_inc_queue_kernel<<<grid, kIncThreads, 0, stream>>>(p);
+    } else if (target_size <= kIncPrivMax) {
         const uint64_t tiles = ceil_div64(size, kIncTile);
         const uint32_t grid = (uint32_t) std::min<uint64_t>(tiles, (uint64_t) dev.sm_count * 8);
         scatter_inc_private_kernel<<<grid, kIncThreads, 0, stream>>>(p);

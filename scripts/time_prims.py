@@ -194,28 +194,29 @@ def main():
             return lambda: [dr.scatter_add(tgt, vals[k], idxs[k]) for k in range(count)]
         return setup
 
-    def s_inc(log2_counters, queue=False):
+    def s_inc(log2_counters, queue=False, masked=False):
         def setup(n):
             B = 1 << log2_counters
             tgt = torch.zeros(B, dtype=torch.int32, device=dev)
             out = torch.empty(n, dtype=torch.int32, device=dev)
             if queue:
-                return lambda: ops.scatter_inc(tgt, None, size=n, out=out)
+                m = None
+                if masked:
+                    m = torch.empty(n, dtype=torch.uint8, device=dev); ops.fill_fmix32(m, 2, and_=128)
+                return lambda: ops.scatter_inc(tgt, None, active=m, size=n, out=out)
             i = torch.empty(n, dtype=torch.int32, device=dev); ops.fill_fmix32(i, 0, xor=7, and_=B - 1)
             return lambda: ops.scatter_inc(tgt, i, out=out)
         return setup
 
-    if want & {"packet", "scatter_inc", "all"}:
-        if want & {"packet", "all"}:
-            run("packet4", 26, 20, s_packet(4, 20), group="packet")                      # 2^26 RGBA samples -> 2^20 pixels
-            run("packet4x1", 26, 32, s_packet(4, 20, four_scalar=True), group="packet")  # the same as four scalar scatters
-            run("packet2", 26, 12, s_packet(2, 20), group="packet")
-            run("packet8", 26, 36, s_packet(8, 20), group="packet")
-        if want & {"scatter_inc", "all"}:
-            run("inc_queue", 28, 4, s_inc(0, queue=True), group="scatter_inc")                # one counter, no index array
-            run("inc_16", 28, 8, s_inc(4), group="scatter_inc")
-            run("inc_2048", 28, 8, s_inc(11), group="scatter_inc")
-            run("inc_2^20", 26, 8, s_inc(20), group="scatter_inc")
+    run("packet4", 26, 20, s_packet(4, 20), group="packet")                      # 2^26 RGBA samples -> 2^20 pixels
+    run("packet4x1", 26, 32, s_packet(4, 20, four_scalar=True), group="packet")  # the same as four scalar scatters
+    run("packet2", 26, 12, s_packet(2, 20), group="packet")
+    run("packet8", 26, 36, s_packet(8, 20), group="packet")
+    run("inc_queue", 28, 4, s_inc(0, queue=True), group="scatter_inc")                # one counter, no index array
+    run("inc_queue_m", 28, 5, s_inc(0, queue=True, masked=True), group="scatter_inc") # the same with a 50 % mask
+    run("inc_16", 28, 8, s_inc(4), group="scatter_inc")
+    run("inc_2048", 28, 8, s_inc(11), group="scatter_inc")
+    run("inc_2^20", 26, 8, s_inc(20), group="scatter_inc")
     if "sort_composed" in want:
         run("sort_composed", 26, 4 * 20, s_sort_composed)
     if "torch_sort" in want:

@@ -170,9 +170,14 @@ def test_scatter_inc_queue_form(n):
     """dr.scatter_inc(counter, 0, active): the slots of the active elements are a permutation of
     start .. start + count - 1 (tests/test_while_loop.py:539 uses it as a queue allocator)"""
     mask = (capi.fmix32(n, xor=5) & 1) != 0
-    for m in (None, mask):
+    for m, misalign in ((None, 0), (mask, 0), (mask, 1), (None, 3)):     # misaligned: element-wise loads / stores
         tgt = to_dev(np.array([7, 99], np.uint32), "u32")
-        out = to_np(dr.scatter_inc(tgt, None, active=None if m is None else torch.from_numpy(m).cuda(), size=n), "u32")
+        d_m = None
+        if m is not None:
+            d_m = torch.zeros(n + misalign, dtype=torch.bool, device="cuda")[misalign:]
+            d_m.copy_(torch.from_numpy(m))
+        d_out = torch.full((n + misalign,), -1, dtype=torch.int32, device="cuda")[misalign:]
+        out = to_np(dr.scatter_inc(tgt, None, active=d_m, size=n, out=d_out), "u32")
         act = np.ones(n, bool) if m is None else m
         cnt = int(act.sum())
         assert to_np(tgt, "u32").tolist() == [7 + cnt, 99]
