@@ -729,6 +729,16 @@ def main():
             cpu_baseline = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"unavailable: {e}"}
 
+    scatter_forms = None
+    if world == 1 and not args.no_extras:
+        try:
+            del wl, prims
+            results.clear()
+            torch.cuda.empty_cache()
+            scatter_forms = time_scatter_forms(torch, ops, dev, peak, args.scale)
+        except Exception as e:  # pragma: no cover  (a side measurement never takes the bench line with it)
+            scatter_forms = {"unavailable": str(e)}
+
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -736,13 +746,52 @@ def main():
         "data": "synthetic (fmix32)", "config": workload_config(args, weak=args.weak, distinct=wl_distinct),
         "frac_of_hbm_peak": round(value / (peak * world), 4), "verified": verified, "verified_primitives": checked,
         "primitives": primitives, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
-        "e2e": e2e, "weak_scaling": weak_scaling, "gpu_launches": launches, "clocks": clocks,
+        "e2e": e2e, "weak_scaling": weak_scaling, "scatter_forms": scatter_forms, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
         comm.destroy()
         dist.destroy_process_group()
+
+
+def time_scatter_forms(torch, ops, dev, peak, scale):
+    """Side measurement (N = 1, NOT part of `value`): the packet form of scatter-reduce and dr.scatter_inc
+    (drjit_b200/csrc/scatter_packet.cu), CUDA events around 10 calls each after 3 warm-ups."""
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    n, pixels = (1 << 26) >> scale, max((1 << 20) >> scale, 16)
+    vals = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(4)]
+    for k, v in enumerate(vals):
+        ops.fill_fmix32(v, 1, xor=k + 1)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    ops.fill_fmix32(idx, 0, xor=0x85EBCA6B, and_=pixels - 1)
+    film = torch.zeros(4 * pixels, dtype=torch.float32, device=dev)
+    ms = timed(lambda: ops.scatter_reduce_packet(1, film, vals, idx))
+    out["scatter_add_packet4_f32"] = {"elements": n, "ms": round(ms, 4), "GBps": round(n * 20 / ms / 1e6, 1),
+                                      "frac_of_peak_per_gpu": round(n * 20 / ms / 1e6 / peak, 4),
+                                      "note": "2^26 four-component packets into 2^20 packets (20 B/element); bound by the L2's 16-byte reduction rate"}
+    del vals, film
+    n = (1 << 28) >> scale
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    ops.fill_fmix32(mask, 2, and_=128)
+    slots = torch.empty(n, dtype=torch.int32, device=dev)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ops.scatter_inc(counter, None, active=mask, size=n, out=slots))
+    out["scatter_inc_queue_masked"] = {"elements": n, "ms": round(ms, 4), "GBps": round(n * 5 / ms / 1e6, 1),
+                                       "frac_of_peak_per_gpu": round(n * 5 / ms / 1e6 / peak, 4),
+                                       "note": "dr.scatter_inc(counter, 0, active) over 2^28 elements, 50 % active (mask byte + slot: 5 B/element)"}
+    return out
 
 
 def run_e2e(args, torch, dist, ops, sh, dev, world, rank, wl, prims, results, total_bytes):
