@@ -454,8 +454,9 @@ scatter_inc_queue_kernel(const IncParams p) {
             bits |= b4 << (4 * r);
         }
         // the next tile's mask words travel while this tile is ranked and stored (loads issued after the
-        // stores queue behind those of the SM's other CTAs: profiles/r6b_ncu_scatter_packet.md)
-        if (p.mask && t + gridDim.x < tiles) fetch(t + gridDim.x, m_n);
+        // stores queue behind those of the SM's other CTAs: profiles/r6b_ncu_scatter_packet.md). Without a
+        // mask array this is pure arithmetic, but it still has to run: the last tile may be a partial one.
+        if (t + gridDim.x < tiles) fetch(t + gridDim.x, m_n);
         const uint32_t count = __popc(bits);
         uint32_t incl = count;
         #pragma unroll

@@ -165,10 +165,12 @@ def test_scatter_inc_reference_grid(B):
             assert np.array_equal(np.sort(exp_out), np.sort(to_np(out, "u32")))
 
 
-@pytest.mark.parametrize("n", [5, 2048, 2049, (1 << 22) + 77])
+@pytest.mark.parametrize("n", [5, 2048, 2049, (1 << 22) + 77, 1184 * 8192 + 8192 + 77])
 def test_scatter_inc_queue_form(n):
     """dr.scatter_inc(counter, 0, active): the slots of the active elements are a permutation of
-    start .. start + count - 1 (tests/test_while_loop.py:539 uses it as a queue allocator)"""
+    start .. start + count - 1 (tests/test_while_loop.py:539 uses it as a queue allocator). The largest
+    size makes the CTAs of a 148-SM grid (8 per SM, 8192-element tiles) walk more than one tile and ends
+    in a partial tile: without a mask array the activity bits of that tile must still be recomputed."""
     mask = (capi.fmix32(n, xor=5) & 1) != 0
     for m, misalign in ((None, 0), (mask, 0), (mask, 1), (None, 3)):     # misaligned: element-wise loads / stores
         tgt = to_dev(np.array([7, 99], np.uint32), "u32")
