@@ -187,6 +187,20 @@ def test_scatter_inc_queue_form(n):
         assert np.all(out[~act] == 0)
 
 
+@pytest.mark.parametrize("B", [7, 4096])
+def test_scatter_inc_ctas_walk_several_tiles(B):
+    """Sizes at which a CTA of the 148-SM grid handles more than one tile / round (shared-memory counters
+    re-zeroed, bases re-fetched, next-tile prefetch) and the last one is partial"""
+    n = 1184 * 2048 + 2048 + 5
+    index = capi.fmix32(n, xor=21) % np.uint32(B)
+    mask = (capi.fmix32(n, xor=22) % np.uint32(5)) != 0
+    before = (np.arange(B, dtype=np.uint32) * 11) % np.uint32(1000)
+    for m in (None, mask):
+        tgt = to_dev(before, "u32")
+        out = dr.scatter_inc(tgt, to_dev(index, "u32"), active=None if m is None else torch.from_numpy(m).cuda())
+        check_scatter_inc(before, to_np(tgt, "u32"), index, m, to_np(out, "u32"), (B, m is not None))
+
+
 def test_scatter_inc_coherent_and_skewed_warps():
     """warps whose lanes agree (one shared-memory atomic), warps with two values, one hot counter"""
     n, B = 1 << 16, 64
