@@ -134,6 +134,22 @@ struct ThreadState {
         check(drjit_b200_scatter_reduce(stream, (int) vt, (int) op, (int) mode, target, target_size,
                                         value, index, mask, size));
     }
+
+    /// Standalone form of the packet scatter-reduce template (src/cuda_packet.cpp:168-327):
+    /// target[index[i] * count + k] op= values[k][i]
+    void scatter_reduce_packet(VarType vt, ReduceOp op, ReduceMode mode, void *target, uint32_t target_packets,
+                               const void *const *values, uint32_t count, const uint32_t *index,
+                               const uint8_t *mask, uint32_t size) {
+        check(drjit_b200_scatter_reduce_packet(stream, (int) vt, (int) op, (int) mode, target, target_packets,
+                                               values, count, index, mask, size));
+    }
+
+    /// Standalone form of the scatter_inc template (src/cuda_scatter.cpp:356-393): out[i] = target[index[i]]++;
+    /// index == nullptr: every active element takes a slot from target[0]
+    void scatter_inc(uint32_t *target, uint32_t target_size, const uint32_t *index, const uint8_t *mask,
+                     uint32_t size, uint32_t *out) {
+        check(drjit_b200_scatter_inc(stream, target, target_size, index, mask, size, out));
+    }
 };
 
 } // namespace drjit_b200

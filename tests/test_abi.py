@@ -115,6 +115,12 @@ int main() {
     ts.block_reduce(VarType::Float32, ReduceOp::Add, 0, 1, buf, buf);
     if (ts.compress((const uint8_t *) buf, 0, buf) != 0) return 7;
     if (ts.block_mkperm(buf, 0, 1, 4, buf, nullptr) != 0) return 8;
+    // scatter forms: an odd packet is rejected like cuda_packet.cpp:184-186; empty inputs are no-ops
+    const void *comps[3] = { buf, buf, buf };
+    try { ts.scatter_reduce_packet(VarType::Float32, ReduceOp::Add, ReduceMode::Auto, buf, 1, comps, 3, buf, nullptr, 1); return 9; }
+    catch (const std::runtime_error &e) { if (!strstr(e.what(), "not supported by reduction")) return 10; }
+    ts.scatter_reduce_packet(VarType::Float32, ReduceOp::Add, ReduceMode::Auto, buf, 1, comps, 2, buf, nullptr, 0);
+    ts.scatter_inc(buf, 1, nullptr, nullptr, 0, buf);
     static_assert(sizeof(AggregationEntry) == 16, "layout");
     static_assert(sizeof(drjit_b200_call_bucket) == 16, "a table row is overwritten in place by a CallBucket");
     return 0;
