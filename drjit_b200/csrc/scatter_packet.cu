@@ -259,6 +259,11 @@ void scatter_reduce_packet(cudaStream_t stream, int vt, int op, int mode, void *
               "reduction (must be even and at most %u)", count, kPkMaxCount);
     if (size == 0)
         return;
+    if (!target || !values || !index)
+        raise(DRJIT_B200_EINVAL, "jit_var_scatter_packet(): null target / values / index array");
+    for (uint32_t k = 0; k < count; ++k)
+        if (!values[k])
+            raise(DRJIT_B200_EINVAL, "jit_var_scatter_packet(): component %u has no data", k);
     PacketParams p{};
     p.target = target; p.index = index; p.mask = mask; p.size = size; p.count = count;
     for (uint32_t k = 0; k < count; ++k) p.values[k] = values[k];
@@ -534,6 +539,8 @@ void scatter_inc(cudaStream_t stream, uint32_t *target, uint32_t target_size, co
         return;
     if (target_size == 0)
         raise(DRJIT_B200_EINVAL, "jit_var_scatter_inc(): the target array is empty");
+    if (!target || !out)
+        raise(DRJIT_B200_EINVAL, "jit_var_scatter_inc(): null target / output array");
     const DeviceProps &dev = device_props();
     IncParams p{};
     p.target = target; p.index = index; p.mask = mask; p.out = out; p.size = size; p.target_size = target_size;

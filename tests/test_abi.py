@@ -121,6 +121,11 @@ int main() {
     catch (const std::runtime_error &e) { if (!strstr(e.what(), "not supported by reduction")) return 10; }
     ts.scatter_reduce_packet(VarType::Float32, ReduceOp::Add, ReduceMode::Auto, buf, 1, comps, 2, buf, nullptr, 0);
     ts.scatter_inc(buf, 1, nullptr, nullptr, 0, buf);
+    const void *hole[2] = { buf, nullptr };
+    try { ts.scatter_reduce_packet(VarType::Float32, ReduceOp::Add, ReduceMode::Auto, buf, 1, hole, 2, buf, nullptr, 4); return 11; }
+    catch (const std::runtime_error &e) { if (!strstr(e.what(), "has no data")) return 12; }
+    try { ts.scatter_inc(buf, 1, nullptr, nullptr, 4, nullptr); return 13; }
+    catch (const std::runtime_error &e) { if (!strstr(e.what(), "null target")) return 14; }
     static_assert(sizeof(AggregationEntry) == 16, "layout");
     static_assert(sizeof(drjit_b200_call_bucket) == 16, "a table row is overwritten in place by a CallBucket");
     return 0;
