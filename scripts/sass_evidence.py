@@ -30,15 +30,21 @@ HOT = [
     "void djb::prefix_group_blocks_kernel<float, djb::OpAdd, 32u, false>",
     "void djb::block_reduce_group_kernel<float, djb::OpAdd, true, false>",
     "void djb::scatter_reduce_kernel<float, djb::OpAdd, false>",
+    "void djb::scatter_packet_vec_kernel<float, djb::OpAdd, 4u, 4u>",
+    "void djb::scatter_packet_kernel<__half, djb::OpAdd, 8u, false>",
+    "djb::scatter_inc_queue_kernel",
+    "djb::scatter_inc_private_kernel",
 ]
 
 CLASSES = [
     ("LDG.E.*STRONG.GPU (descriptors)", re.compile(r"\bLDG\.E\.\S*STRONG\.GPU")),
-    ("LDG.E.128", re.compile(r"\bLDG\.E\.128")),
+    ("LDG.E.*128 (128-bit global loads)", re.compile(r"\bLDG\.E\.(?:(?!STRONG)\S)*128")),
     ("LDS.128", re.compile(r"\bLDS\.128")),
-    ("STG.E.128", re.compile(r"\bSTG\.E\.128")),
+    ("STG.E.*128 (128-bit global stores)", re.compile(r"\bSTG\.E\.\S*128")),
     ("ATOMS (shared atomics)", re.compile(r"\bATOMS")),
     ("RED/REDG (global reductions)", re.compile(r"\bREDG?\.E")),
+    ("REDG vector forms (F32x2/x4, F16x4/x8)", re.compile(r"\bREDG\.E\.\w+\.F(32x[24]|16x[48])")),
+    ("MATCH (match.any / match.all)", re.compile(r"\bMATCH\.")),
     ("REDUX (redux.sync)", re.compile(r"\bC?REDUX")),
     ("SHFL", re.compile(r"\bSHFL")),
     ("VOTE", re.compile(r"\bVOTEU?\b")),
